@@ -1,0 +1,125 @@
+"""Pins oracle/agrep_oracle.c against the UNMODIFIED reference built from /root/reference by
+oracle/Makefile (oracle/_ref/agrep).  Skipped when the reference binary is absent (GPU box keeps the
+prebuilt one, so this also runs there).  Reference invocations follow SURVEY.md 8(c):
+k>0 automaton forced with -n, unit-cost asearch1 with -S1, simple literals via sgrep/bm."""
+import os, random, re, subprocess, tempfile
+import pytest
+import _oracle, _corpus
+
+
+def run_ref(ref, args, data):
+    with tempfile.NamedTemporaryFile(suffix=".txt", delete=False) as f:
+        f.write(data)
+        path = f.name
+    try:
+        p = subprocess.run([ref, "-V0"] + args + [path], capture_output=True, timeout=120)
+        return p.stdout
+    finally:
+        os.unlink(path)
+
+
+def ref_count(ref, args, data):
+    out = run_ref(ref, ["-c"] + args, data).strip()
+    return int(out) if out else 0
+
+
+def ref_ordinals(ref, args, data):
+    out = run_ref(ref, ["-n"] + args, data)
+    return [int(m.group(1)) for m in re.finditer(rb"^(\d+): ", out, re.M)]
+
+
+TEXT = _corpus.make_text(4000, seed=12345)
+TEXT_NONL = _corpus.make_text(500, seed=7, trailing_newline=False)
+PARA = _corpus.make_text(3000, seed=99, paragraphs=True)
+
+CASES = [
+    # (pattern, oracle kwargs, reference args)
+    ("because each", dict(k=0, linenum=1), []),
+    ("because each", dict(k=1, linenum=1), ["-1"]),
+    ("because each", dict(k=2, linenum=1), ["-2"]),
+    ("government", dict(k=3, linenum=1), ["-3"]),
+    ("governmental", dict(k=4, linenum=1, nocase=1), ["-4", "-i"]),
+    ("governmental", dict(k=5, linenum=1), ["-5"]),
+    ("homogeneous approx", dict(k=8, linenum=1), ["-8"]),
+    ("matching", dict(k=1, linenum=1, wordbound=1), ["-1", "-w"]),
+    ("the", dict(k=0, linenum=1, wordbound=1), ["-w"]),
+    ("pattern string", dict(k=2, linenum=1, inverse=1), ["-2", "-v"]),
+    ("pat[a-t]ern", dict(k=1, linenum=1), ["-1"]),
+    ("st.ing", dict(k=0, linenum=1), []),
+    ("<algo>rithm", dict(k=2, linenum=1), ["-2"]),
+    ("^the", dict(k=0, linenum=1), []),
+    ("world$", dict(k=1, linenum=1), ["-1"]),
+    ("state;world", dict(k=0, linenum=1), []),
+    ("[^a-s]he ", dict(k=0, linenum=1), []),
+    ("between both life", dict(k=2, linenum=1, cost_s=1), ["-2", "-S1"]),
+    ("between both life", dict(k=3, linenum=1, cost_s=2), ["-3", "-S2"]),
+    ("between both life", dict(k=3, linenum=1, cost_i=2, cost_d=3), ["-3", "-I2", "-D3"]),
+    ("government", dict(k=2, linenum=1, ins_free=1), ["-2", "-p"]),
+    ("a#t", dict(k=0, linenum=1), []),
+]
+
+
+@pytest.mark.parametrize("pattern,okw,rargs", CASES)
+@pytest.mark.parametrize("which", ["nl", "nonl"])
+def test_automaton_matches_reference(ref_agrep, pattern, okw, rargs, which):
+    if not ref_agrep:
+        pytest.skip("reference binary not built")
+    data = TEXT if which == "nl" else TEXT_NONL
+    a = _oracle.compile(pattern, width=32, **okw)
+    cnt, recs = _oracle.scan(a, data)
+    assert cnt == ref_count(ref_agrep, ["-n"] + rargs + [pattern], data)
+    # -n prints j-1 (agrep.c:3878)
+    assert [r[2] - 1 for r in recs] == ref_ordinals(ref_agrep, rargs + [pattern], data)
+
+
+@pytest.mark.parametrize("pattern,k", [("win", 0), ("because each", 2), ("state", 1)])
+def test_paragraph_records(ref_agrep, pattern, k):
+    if not ref_agrep:
+        pytest.skip("reference binary not built")
+    a = _oracle.compile(pattern, width=32, k=k, linenum=1, wordbound=1, delim="$$")
+    cnt, recs = _oracle.scan(a, PARA)
+    assert cnt == ref_count(ref_agrep, ["-n", "-w", "-d", "$$", "-%d" % k, pattern] if k else ["-n", "-w", "-d", "$$", pattern], PARA)
+
+
+@pytest.mark.parametrize("pattern,kw,rargs", [
+    ("the", {}, []), ("The", {}, []), ("government", {}, []), ("the", dict(wordbound=1), ["-w"]),
+    ("each", dict(nocase=1), ["-i"]), ("zzzz", {}, [])])
+@pytest.mark.parametrize("which", ["nl", "nonl"])
+def test_sgrep_bm_counts(ref_agrep, pattern, kw, rargs, which):
+    """config 1: `agrep -c the` goes through sgrep()->bm() (case-insensitive substring, once per line)."""
+    if not ref_agrep:
+        pytest.skip("reference binary not built")
+    data = TEXT if which == "nl" else TEXT_NONL
+    a = _oracle.compile(pattern, **kw)
+    assert a.engine == 4
+    cnt, _ = _oracle.scan(a, data, want_records=False)
+    assert cnt == ref_count(ref_agrep, rargs + [pattern], data)
+
+
+def test_random_differential(ref_agrep):
+    """SURVEY appendix A differential driver: random substrings with 0-2 edits, k in 1..3, -n forced."""
+    if not ref_agrep:
+        pytest.skip("reference binary not built")
+    rnd = random.Random(2024)
+    lines = TEXT.decode().split("\n")
+    for trial in range(40):
+        ln = rnd.choice([l for l in lines if len(l) > 40])
+        m = rnd.choice([4, 6, 8, 12, 16, 20, 24, 27])
+        st = rnd.randrange(len(ln) - m)
+        pat = _corpus.mutate(rnd, ln[st:st + m], rnd.randint(0, 2))
+        if any(ch in pat for ch in ";,.*-[]()<>|#{}~^$\\"):
+            continue
+        k = rnd.randint(1, 3)
+        if len(pat) <= k:
+            continue
+        a = _oracle.compile(pat, width=32, k=k, linenum=1)
+        cnt, recs = _oracle.scan(a, TEXT)
+        assert [r[2] - 1 for r in recs] == ref_ordinals(ref_agrep, ["-%d" % k, pat], TEXT), (pat, k)
+
+
+def test_pattern_too_long_matches_reference_limit():
+    # maskgen.c:201-208: literal of 30 chars -> M = 32 -> rejected at width 32; fine at width 64
+    with pytest.raises(_oracle.OracleError):
+        _oracle.compile("a" * 30, width=32, k=1, linenum=1)
+    _oracle.compile("a" * 29, width=32, k=1, linenum=1)
+    _oracle.compile("a" * 40, width=64, k=1, linenum=1)
