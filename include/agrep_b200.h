@@ -1,0 +1,165 @@
+/* include/agrep_b200.h -- C ABI of libagrepb200.so: the B200 scan engine behind agrep's scan path.
+ *
+ * Plain C, pointers and sizes only.  Two layers:
+ *
+ *  (1) The reentrant engine ABI (agb_*): an explicit scan descriptor (the words the reference keeps in
+ *      globals: Mask[], Init[0], Init1, NO_ERR_MASK, endposition, D_endpos -- agrep.c:135-140 -- plus the
+ *      flags the scan loops read) and a scan call over a device or host text span that returns the
+ *      number of matching records and, on request, the ordered list of matching records in the exact
+ *      (lasti, print_end, j) terms the reference hands to output() (bitap.c:212-214, asearch.c:162-168).
+ *
+ *  (2) The drop-in layer (libagrepb200_dropin.so, declared in agrep_b200_dropin.h): bitap(), asearch(),
+ *      asearch0(), asearch1(), sgrep(), fill_buf(), alloc_buf(), free_buf() with the reference's own
+ *      signatures, reading the reference's globals, so the reference's exec() links against it unchanged.
+ *
+ * There is no CPU fallback: every agb_scan_* call runs the sm_100a kernels and fails with
+ * AGB_ERR_CUDA when no device is usable.
+ */
+#ifndef AGREP_B200_H
+#define AGREP_B200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGB_MAXERR    8     /* MaxError, reference agrep.h:45 */
+#define AGB_MAXDELIM  8     /* MAXDELIM, reference agrep.h:35 */
+#define AGB_MAXANCHOR 24
+
+enum {
+	AGB_OK = 0,
+	AGB_ERR_PATTERN = -1,   /* pattern rejected; message in the err buffer (the reference prints it and returns -1) */
+	AGB_ERR_CUDA = -2,      /* CUDA runtime error / no device; message via agb_last_error() */
+	AGB_ERR_ARG = -3,
+	AGB_ERR_NOMEM = -4
+};
+
+/* The subset of agrep's command line that reaches the scan path (reference agrep.c:2121-2739). */
+typedef struct agb_options {
+	int32_t k;            /* -#  number of errors D (0..8)                                   */
+	int32_t nocase;       /* -i  NOUPPER                                                     */
+	int32_t wordbound;    /* -w  WORDBOUND                                                   */
+	int32_t wholeline;    /* -x  WHOLELINE                                                   */
+	int32_t inverse;      /* -v  INVERSE                                                     */
+	int32_t linenum;      /* -n  LINENUM: forces the bitap family (checksg.c:132)            */
+	int32_t ins_free;     /* -p  I = 0                                                       */
+	int32_t cost_i, cost_s, cost_d;   /* -I# -S# -D# ; 0 = not given                         */
+	int32_t bestmatch;    /* -B  BESTMATCH: forces the bitap family (checksg.c:127)          */
+	int32_t reserved;
+	const char *delim;    /* -d  argument as typed, NULL = newline records                   */
+} agb_options;
+
+/* engines = which reference function the descriptor stands for */
+enum { AGB_ENGINE_BITAP = 0,    /* bitap.c:169-284   exact shift-and                          */
+       AGB_ENGINE_ASEARCH = 1,  /* asearch.c:94-306  k = 1..4                                 */
+       AGB_ENGINE_ASEARCH0 = 2, /* asearch.c:620-774 k = 5..8                                 */
+       AGB_ENGINE_ASEARCH1 = 3, /* asearch1.c:86-235 non-unit costs                           */
+       AGB_ENGINE_SGREP_BM = 4  /* sgrep.c:262 + bm() sgrep.c:694: simple literal, k = 0      */ };
+
+/* front-end plan chosen by agb_compile for the device scan */
+enum { AGB_PLAN_ALL = 0,        /* every 16-byte chunk goes to the record stage               */
+       AGB_PLAN_ANCHORS = 1     /* pigeonhole pre-filter on k+1 disjoint literal anchors      */ };
+
+/* The scan descriptor.  64-bit words, LSB aligned: pattern position p (1-based, delimiter first)
+ * lives at bit M-p, bits >= M are the always-on feed (reference maskgen.c:218-234 with WORD=64). */
+typedef struct agb_desc {
+	uint64_t mask[256];       /* Mask[c]; for AGB_ENGINE_BITAP with -i the LUT[] of bitap.c:171 is pre-folded */
+	uint64_t init0, init1, noerr, endpos, dendpos, dmask, wildmask;
+	uint64_t reset[2 * AGB_MAXERR + 1]; /* rows right after a record closes (asearch.c:175-186), a constant */
+	uint64_t start[2 * AGB_MAXERR + 1]; /* rows after the virtual leading '\n' when it does NOT close a record */
+	int32_t  start_closes;    /* 1: the virtual '\n' closes a (never reported) record, scan starts from reset[] */
+	int32_t  M, L;            /* positions; delimiter length                                  */
+	uint8_t  delim[2 * AGB_MAXDELIM + 2];
+	int32_t  delim_kind;      /* 0: border-free (every occurrence closes a record); 1: c^L run rule */
+	int32_t  k;               /* error rows                                                   */
+	int32_t  nrows;           /* k+1, or 2k+1 for ASEARCH1 (rows k..2k live)                  */
+	int32_t  cost_i, cost_s, cost_d;
+	int32_t  engine, and_mode, inverse, user_delim, outtail;
+	/* plan */
+	int32_t  plan;
+	int32_t  n_anchors, anchor_len;           /* anchor_len in 2..4 bytes                    */
+	uint32_t anchor[AGB_MAXANCHOR];           /* little-endian packed anchor bytes           */
+	uint32_t anchor_fold;                     /* OR-mask applied to text and anchors (0x20 per letter byte under -i / bm) */
+	uint32_t anchor_mask;                     /* 0xFFFFFFFF, 0x00FFFFFF or 0x0000FFFF        */
+} agb_desc;
+
+typedef struct agb_pattern agb_pattern;       /* opaque: agb_desc + bookkeeping              */
+
+/* one matching record, in the reference's own terms (file offsets, not buffer indexes):
+ *   begin   = offset of lasti: first byte of the delimiter that closed the previous record; -1 for the
+ *             virtual '\n' in front of the text (bitap.c:140), 0 when a user delimiter has not been seen yet
+ *   end     = offset of print_end + 1 = first byte of the delimiter that closes this record
+ *   ordinal = j at output() time; -n prints j-1 (agrep.c:3878); 0 unless AGB_WANT_ORDINALS
+ *   level   = smallest matching error level in best-match scans, else k                                */
+typedef struct agb_record {
+	int64_t begin;
+	int64_t end;
+	int64_t ordinal;
+	int32_t level;
+	int32_t pad;
+} agb_record;
+
+enum { AGB_WANT_COUNT = 0, AGB_WANT_RECORDS = 1, AGB_WANT_ORDINALS = 2, AGB_WANT_LEVELS = 4 };
+
+typedef struct agb_result {
+	uint64_t n_matched;       /* num_of_matched for this text                                 */
+	uint64_t n_records;       /* entries written to records (<= capacity)                     */
+	uint64_t n_flagged;       /* 16-byte chunks the front-end passed to the record stage      */
+	uint64_t level_hist[AGB_MAXERR + 1];      /* AGB_WANT_LEVELS: records by smallest level   */
+	float    ms_front, ms_records;            /* device time of the two stages (CUDA events)  */
+} agb_result;
+
+/* ---- pattern front-end (host; mirrors checksg.c + preproce.c + maskgen.c) ---- */
+int  agb_compile(const char *pattern, const agb_options *opt, agb_pattern **out, char *err, size_t errlen);
+void agb_pattern_free(agb_pattern *p);
+const agb_desc *agb_pattern_desc(const agb_pattern *p);
+/* wrap words produced elsewhere (the drop-in layer passes the reference's globals); plan = AGB_PLAN_ALL */
+int  agb_pattern_from_desc(const agb_desc *d, agb_pattern **out, char *err, size_t errlen);
+
+/* ---- device scan ----
+ * d_text: device pointer, 16-byte aligned, readable up to the next 16-byte boundary after n.
+ * d_records: device buffer for agb_record[capacity] (may be NULL with AGB_WANT_COUNT).
+ * stream: cudaStream_t as void* (NULL = default stream).  The call is synchronous w.r.t. the host
+ * only for the 64-byte result read-back. */
+int  agb_scan_device(const agb_pattern *p, const void *d_text, uint64_t n, int want,
+                     agb_record *d_records, uint64_t capacity, void *stream, agb_result *res);
+
+/* host text: staged through pinned buffers in slices cut at record boundaries, H2D overlapped with the
+ * scan (the fill_buf replacement, bitap.c:450-477).  records: host array. */
+int  agb_scan_host(const agb_pattern *p, const void *h_text, uint64_t n, int want,
+                   agb_record *records, uint64_t capacity, agb_result *res);
+
+/* file descriptor: read(2) loop into the pinned ring, as agb_scan_host */
+int  agb_scan_fd(const agb_pattern *p, int fd, int want, agb_record *records, uint64_t capacity, agb_result *res);
+
+/* the -B sweep of agrep.c:3582-3728 as ONE extra pass: smallest k in 1..min(M-1,8) with a match */
+int  agb_bestmatch_device(const char *pattern, const agb_options *opt, const void *d_text, uint64_t n,
+                          void *stream, int *best_k, agb_result *res, char *err, size_t errlen);
+
+/* ---- synthetic corpus (bench / tests): deterministic, identical on host and device ---- */
+typedef struct agb_corpus_spec {
+	uint64_t seed;
+	uint64_t n_bytes;          /* multiple of 4096                                            */
+	uint64_t first_page;       /* page index of byte 0 (sharding)                             */
+	int32_t  paragraphs;       /* 1: blank line every 3..8 lines                              */
+	int32_t  needle_every;     /* a planted line every this many pages (0 = none)             */
+	char     needle[64];       /* the pattern to plant, edited 0..needle_maxedits times       */
+	int32_t  needle_maxedits;
+	int32_t  pad;
+} agb_corpus_spec;
+int  agb_corpus_fill_device(const agb_corpus_spec *s, void *d_text, void *stream);
+int  agb_corpus_fill_host(const agb_corpus_spec *s, void *h_text);
+
+/* ---- misc ---- */
+const char *agb_last_error(void);
+int  agb_device_count(void);
+int  agb_set_device(int dev);
+const char *agb_version(void);
+uint64_t agb_kernel_launches(void);   /* kernels this process launched through the library so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

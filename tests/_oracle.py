@@ -25,7 +25,7 @@ class Automaton(C.Structure):
 
 
 class Record(C.Structure):
-    _fields_ = [("begin", C.c_uint64), ("end", C.c_uint64), ("ordinal", C.c_int64), ("level", C.c_int)]
+    _fields_ = [("begin", C.c_int64), ("end", C.c_int64), ("ordinal", C.c_int64), ("level", C.c_int)]
 
 
 def lib():

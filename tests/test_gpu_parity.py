@@ -1,0 +1,148 @@
+"""GPU parity: the CUDA path (through the C ABI, host-buffer entry agb_scan_host) against the oracle on the
+same inputs, and against the committed golden vectors of the real reference.  Bit-exact: counts and the
+ordered (lasti, print_end) lists."""
+import json, os, random
+import pytest
+import _oracle, _corpus
+import agrep_b200 as ag
+from test_oracle_golden import G, CORPORA, text
+
+pytestmark = pytest.mark.gpu
+
+
+def api_kw(okw):
+    return {k: v for k, v in okw.items() if k != "width"}
+
+
+def check(pattern, data, **kw):
+    a = _oracle.compile(pattern, **kw)
+    cnt, recs = _oracle.scan(a, data)
+    p = ag.Pattern(pattern, **api_kw(kw))
+    res, got = p.scan_host(data)
+    assert res.n_matched == cnt, (pattern, kw, res.n_matched, cnt)
+    assert [(b, e) for b, e, _, _ in got] == [(b, e) for b, e, _ in recs], (pattern, kw)
+    res2, _ = p.scan_host(data, want_records=False)
+    assert res2.n_matched == cnt
+    return res
+
+
+@pytest.mark.parametrize("name", sorted(G["scan"]))
+def test_golden_case(name):
+    c = G["scan"][name]
+    kw = dict(c["api"])
+    res = check(c["pattern"], text(c["corpus"]), **kw)
+    assert res.n_matched == c["count"]          # the real reference's answer
+
+
+TEXT = _corpus.make_text(4000, seed=12345)
+
+
+def test_random_differential():
+    rnd = random.Random(77)
+    lines = TEXT.decode().split("\n")
+    n = 0
+    while n < 60:
+        ln = rnd.choice([l for l in lines if len(l) > 40])
+        m = rnd.choice([3, 4, 5, 6, 8, 12, 16, 20, 24, 27, 33, 40])
+        if m >= len(ln):
+            continue
+        st = rnd.randrange(len(ln) - m)
+        pat = _corpus.mutate(rnd, ln[st:st + m], rnd.randint(0, 2))
+        if any(ch in pat for ch in ";,.*-[]()<>|#{}~^$\\"):
+            continue
+        k = rnd.randint(0, min(4, len(pat) - 1))
+        kw = dict(k=k, linenum=1)
+        if rnd.random() < 0.3: kw["nocase"] = 1
+        if rnd.random() < 0.2: kw["wordbound"] = 1
+        check(pat, TEXT, **kw)
+        n += 1
+
+
+@pytest.mark.parametrize("data", [
+    b"", b"\n", b"a", b"abc", b"abc\n", b"\nabc", b"\n\n\n", b"xabcx", b"ab\ncab\nc\n", b"abc\nabc\nabc",
+    b"ab" + b"c" * 15 + b"\n", b"x" * 15 + b"abc\n", b"x" * 14 + b"abc\n" + b"y" * 40 + b"\nabc",
+    b"x" * 5000 + b"abc" + b"y" * 5000 + b"\nzzz\n", b"\n" * 100 + b"abc" + b"\n" * 100])
+@pytest.mark.parametrize("kw", [dict(k=0, linenum=1), dict(k=1, linenum=1), dict(k=0), dict(k=0, linenum=1, inverse=1),
+                                dict(k=2, linenum=1, wordbound=1)])
+def test_edges(data, kw):
+    check("abc", data, **kw)
+
+
+@pytest.mark.parametrize("delim,kw", [("$$", dict(k=1)), ("$$", dict(k=0, wordbound=1)), ("the", dict(k=1)),
+                                       ("ab", dict(k=0)), ("\\.", dict(k=2)), ("$$", dict(k=2, inverse=1))])
+def test_user_delimiters(delim, kw):
+    para = _corpus.make_text(1500, seed=5, paragraphs=True)
+    for data in (para, para + b"\n", b"\n\n" + para, para[:-1], b"\n\n\n\n\n" + para + b"\n\n\n"):
+        check("because", data, linenum=1, delim=delim, **kw)
+        check("state good", data, linenum=1, delim=delim, **kw)
+
+
+def test_long_records_and_no_delimiter():
+    rnd = random.Random(3)
+    body = bytes(rnd.choice(b"abcdefghij ") for _ in range(300000))
+    for data in (body, body + b"\n", body[:150000] + b"\n" + body[150000:], body.replace(b"j", b"\n")):
+        check("abcde", data, k=1, linenum=1)
+        check("fgh", data, k=0)
+        check("a[bc]d", data, k=0, linenum=1)       # no anchors: every chunk goes to the record stage
+
+
+def test_wide_pattern_64bit_rows():
+    pat = "people how too little state good very make"      # 42 chars -> M = 44
+    data = TEXT + b"xx people how too little state good very make yy\nxx people hxw too litle state good very make\n"
+    for k in (0, 1, 2, 3):
+        res = check(pat, data, k=k, linenum=1)
+    assert res.n_matched >= 2
+
+
+def test_costs_and_insfree():
+    check("between both life", TEXT, k=3, linenum=1, cost_s=2)
+    check("between both life", TEXT, k=3, linenum=1, cost_i=2, cost_d=3)
+    check("government", TEXT, k=2, linenum=1, ins_free=1)
+    check("gover#ment;world", TEXT, k=1, linenum=1)
+
+
+def test_levels_histogram():
+    a = _oracle.compile("governmental", k=4, linenum=1)
+    cnt, hist, recs = _oracle.scan_levels(a, 4, TEXT)
+    p = ag.Pattern("governmental", k=4, linenum=1)
+    res, got = p.scan_host(TEXT, levels=True)
+    assert list(res.level_hist)[:5] == hist[:5]
+    assert res.n_matched == cnt
+    assert [(b, e, l) for b, e, _, l in got] == [(b, e, l) for b, e, _, l in recs]
+
+
+def test_device_corpus_equals_host_corpus_and_device_scan():
+    import torch
+    n = 256 * 4096
+    t = torch.empty(n + 64, dtype=torch.uint8, device="cuda")
+    ag.corpus_device(t.data_ptr(), n, needle="because each", needle_every=8, needle_maxedits=3)
+    torch.cuda.synchronize()
+    host = ag.corpus_host(n, needle="because each", needle_every=8, needle_maxedits=3)
+    assert bytes(t[:n].cpu().numpy().tobytes()) == host
+    for k in (0, 1, 2, 3):
+        a = _oracle.compile("because each", k=k, linenum=1)
+        cnt, _ = _oracle.scan(a, host, want_records=False)
+        p = ag.Pattern("because each", k=k, linenum=1)
+        res = p.scan_device(t.data_ptr(), n)
+        assert res.n_matched == cnt
+        assert res.n_flagged < n // 16 // 20     # the anchor filter is selective on this text
+
+
+def test_bestmatch_sweep():
+    import torch
+    host = ag.corpus_host(64 * 4096)
+    t = torch.frombuffer(bytearray(host + b"\0" * 64), dtype=torch.uint8).cuda()
+    for pat in ("goverment of the peple", "because each", "zzzzqqqqxxxx"):
+        a0 = _oracle.compile(pat, k=0, linenum=1, nocase=1)
+        want = -1
+        for k in range(0, min(8, len(pat) - 1) + 1):
+            a = _oracle.compile(pat, k=k, linenum=1, nocase=1)
+            cnt, _ = _oracle.scan(a, host, want_records=False)
+            if cnt:
+                want = (k, cnt)
+                break
+        best, res = ag.bestmatch_device(pat, t.data_ptr(), len(host), nocase=1)
+        if want == -1:
+            assert best == -1
+        else:
+            assert (best, res.n_matched) == want

@@ -1,0 +1,126 @@
+"""Host-side checks of the product's pattern front-end (agrep_b200/csrc/pattern.c) -- no GPU needed:
+ * the descriptor words equal the reference's globals after maskgen() (golden dumps from the real reference);
+ * they equal the oracle's independent restatement, also beyond 32 positions;
+ * the C ABI library loads and exports every symbol include/agrep_b200.h declares."""
+import ctypes, json, os, random, re
+import pytest
+import _oracle, _corpus
+import agrep_b200 as ag
+from agrep_b200 import _lib
+from test_oracle_golden import G, _args_to_kw
+
+LUT = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "lut_lower1.json")))
+
+
+def api_kw(okw):
+    kw = {k: v for k, v in okw.items() if k != "width"}
+    return kw
+
+
+def test_library_exports_declared_symbols():
+    L = _lib.lib()
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(__file__)), "include", "agrep_b200.h")).read()
+    declared = set(re.findall(r"\b(agb_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(L, name), name
+    assert set(_lib.EXPORTS) <= declared
+    assert b"sm_100a" in L.agb_version()
+
+
+@pytest.mark.parametrize("name", sorted(G["dump"]))
+def test_words_equal_reference_globals(name):
+    d = G["dump"][name]
+    kw = api_kw(_args_to_kw(d["ref_args"]))
+    p = ag.Pattern(d["pattern"], **kw)
+    D = p.desc
+    m32 = 0xFFFFFFFF
+    assert D.M == d["M"]
+    assert D.init0 & m32 == d["Init0"]
+    assert D.init1 & m32 == d["Init1"]
+    assert D.noerr & m32 == d["NO_ERR_MASK"]
+    assert D.endpos == d["endposition"]
+    assert D.dendpos == d["D_endpos"]
+    assert D.wildmask == d["wildmask"]
+    assert D.and_mode == d["AND"]
+    fold = D.engine == 0 and kw.get("nocase")           # bitap.c:171 applies LUT[] before Mask[]
+    for c in range(256):
+        src = LUT[c] if fold else c
+        assert D.mask[c] == d["mask"].get(str(src), 0), c
+    # upper halves: the always-on feed continues to bit 63
+    assert D.init0 >> 32 == m32 and D.init1 >> 32 == m32 and D.noerr >> 32 == m32
+
+
+PATTERNS = ["abc", "because each", "pat[a-t]ern", "<algo>rithm", "state;world", "state,world;", "a#t", "st.ing", "^the",
+            "world$", "The World", "[^a-s]he ", "x[a\\-c]y", "x[\\]a]y", "a\\.b\\;c", "(ab)c", "[A-Z]x", "ab[.]c", "q<ab>#c",
+            "people how too little state good very make world", "a,b,c", "[a-cx-z0-9]+", "one;two;three"]
+OPTS = [dict(), dict(k=1), dict(k=2, nocase=1), dict(k=3, wordbound=1), dict(k=1, wholeline=1), dict(k=2, delim="$$"),
+        dict(k=1, delim="the"), dict(k=2, ins_free=1), dict(k=3, cost_i=2, cost_d=3), dict(k=2, cost_s=2, inverse=1),
+        dict(k=0, nocase=1), dict(k=0, delim="\\<x")]
+
+
+@pytest.mark.parametrize("pattern", PATTERNS)
+@pytest.mark.parametrize("oi", range(len(OPTS)))
+def test_words_equal_oracle(pattern, oi):
+    okw = dict(OPTS[oi], linenum=1)
+    try:
+        a = _oracle.compile(pattern, **okw)
+    except _oracle.OracleError as e:
+        with pytest.raises(ag.AgrepError):
+            ag.Pattern(pattern, **okw)
+        return
+    D = ag.Pattern(pattern, **okw).desc
+    assert (D.M, D.L, D.k, D.and_mode, D.engine) == (a.M, a.L, a.k, a.and_mode, a.engine)
+    for f in ("init0", "init1", "noerr", "endpos", "dendpos", "dmask", "wildmask"):
+        assert getattr(D, f) == getattr(a, f), f
+    lut = LUT if (a.engine == 0 and okw.get("nocase")) else list(range(256))
+    for c in range(256):
+        assert D.mask[c] == a.mask[lut[c]], c
+    assert bytes(D.delim[:D.L]) == bytes(a.dpat[:a.L])
+
+
+def test_engine_selection_follows_checksg():
+    E = lambda *a, **k: ag.Pattern(*a, **k).desc.engine
+    assert E("the") == 4 and E("the", nocase=1) == 4 and E("the", wordbound=1) == 4      # sgrep/bm
+    assert E("the", linenum=1) == 0 and E("th.e") == 0 and E("^the") == 0              # bitap exact
+    assert E("the", bestmatch=1) == 0
+    assert E("hello", k=1) == 1 and E("hello", k=4, nocase=1) == 1                      # asearch
+    assert E("hello world", k=5) == 2 and E("hello world", k=8) == 2                    # asearch0
+    assert E("hello", k=2, cost_s=2) == 3                                               # asearch1
+    with pytest.raises(ag.AgrepError):
+        ag.Pattern("ab", k=2)            # checksg.c:34
+    with pytest.raises(ag.AgrepError):
+        ag.Pattern("a*b")                # regular expressions are outside the path
+    with pytest.raises(ag.AgrepError):
+        ag.Pattern("a" * 63, k=1, linenum=1)   # 1 + 1 + 63 positions > 63
+    assert ag.Pattern("a" * 61, k=1, linenum=1).desc.M == 63
+
+
+def test_anchor_plan():
+    d = ag.Pattern("because each", k=2).desc
+    assert d.plan == ag.api.PLAN_ANCHORS and d.n_anchors == 3 and d.anchor_len == 4
+    assert [d.anchor[i].to_bytes(4, "little") for i in range(3)] == [b"beca", b"use ", b"each"]
+    d = ag.Pattern("because each", k=3).desc           # 4 runs of 3
+    assert d.n_anchors == 4 and d.anchor_len == 3 and d.anchor_mask == 0xFFFFFF
+    d = ag.Pattern("the").desc                          # bm: always case folded
+    assert d.n_anchors == 1 and d.anchor_len == 3 and d.anchor_fold == 0x202020
+    assert ag.Pattern("because each", k=2, inverse=1).desc.plan == ag.api.PLAN_ALL
+    assert ag.Pattern("government", k=2, ins_free=1).desc.plan == ag.api.PLAN_ALL
+    assert ag.Pattern("a.b.c.d", k=1, linenum=1).desc.plan == ag.api.PLAN_ALL
+    d = ag.Pattern("state,world", linenum=1).desc       # OR: one anchor per alternative
+    assert d.n_anchors == 2
+    d = ag.Pattern("Hello World", k=1, nocase=1).desc
+    assert d.anchor_fold != 0 and all((d.anchor[i] & d.anchor_fold) == d.anchor_fold for i in range(d.n_anchors))
+
+
+def test_corpus_generator_properties():
+    c = ag.corpus_host(64 * 4096, needle="because each", needle_every=4, needle_maxedits=3)
+    assert len(c) == 64 * 4096 and c.count(b"\0") == 0 and max(c) < 128
+    for pg in range(64):
+        assert c[pg * 4096 + 4095] == 10
+    assert c == ag.corpus_host(64 * 4096, needle="because each", needle_every=4, needle_maxedits=3)
+    # shards are position independent
+    assert c[16 * 4096:32 * 4096] == ag.corpus_host(16 * 4096, first_page=16, needle="because each", needle_every=4, needle_maxedits=3)
+    assert c.count(b"because each") >= 4
+    p = ag.corpus_host(16 * 4096, paragraphs=True)
+    assert b"\n\n" in p
