@@ -31,7 +31,8 @@ class Desc(C.Structure):
                 ("engine", C.c_int32), ("and_mode", C.c_int32), ("inverse", C.c_int32),
                 ("user_delim", C.c_int32), ("outtail", C.c_int32),
                 ("plan", C.c_int32), ("n_anchors", C.c_int32), ("anchor_len", C.c_int32),
-                ("anchor", C.c_uint32 * AGB_MAXANCHOR), ("anchor_fold", C.c_uint32), ("anchor_mask", C.c_uint32)]
+                ("anchor", C.c_uint32 * AGB_MAXANCHOR), ("anchor_fold", C.c_uint32), ("anchor_mask", C.c_uint32),
+                ("refine", C.c_int32), ("pat_len", C.c_int32), ("anchor_off", C.c_int32 * AGB_MAXANCHOR)]
 
 
 class Record(C.Structure):

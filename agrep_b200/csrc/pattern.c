@@ -302,7 +302,7 @@ int agbi_derive(agb_desc *d, char *err, size_t errlen)
 
 /* pigeonhole anchor plan: k errors can damage at most k of k+1 disjoint runs of consecutive literal
  * positions, so a matching record contains one run verbatim (the idea of sgrep.c:1053-1154, made exact). */
-static int collect_runs(const build_t *b, int part, int A, uint32_t *out, int cap)
+static int collect_runs(const build_t *b, int part, int A, uint32_t *out, int *where, int cap)
 {
 	int p, run = 0, n = 0;
 	for (p = 1; p <= b->n; p++) {
@@ -311,7 +311,7 @@ static int collect_runs(const build_t *b, int part, int A, uint32_t *out, int ca
 		if (++run == A) {
 			uint32_t v = 0; int t;
 			for (t = 0; t < A; t++) v |= (uint32_t)(b->p[p - A + 1 + t].lit & 0xFF) << (8 * t);
-			if (n < cap) out[n++] = v;
+			if (n < cap) { where[n] = p - A + 1; out[n++] = v; }
 			run = 0;
 		}
 		if (q->wild) run = 0;     /* '#' behind q: free insertions there, a verbatim run cannot continue through it */
@@ -325,32 +325,39 @@ static void plan_anchors(const build_t *b, agb_desc *d, const agb_options *o, in
 	d->plan = AGB_PLAN_ALL; d->n_anchors = 0;
 	if (d->inverse || o->ins_free) return;   /* -v reports the NON-matching records; -p makes insertions free */
 	for (A = 4; A >= 2; A--) {
-		uint32_t got[AGB_MAXANCHOR]; int ngot = 0, ok = 1;
+		uint32_t got[AGB_MAXANCHOR]; int pos[AGB_MAXANCHOR], ngot = 0, ok = 1;
 		if (b->or_seen) {                    /* a,b : any alternative may match -> k+1 runs from each */
 			for (part = 1; part <= b->nparts && ok; part++) {
-				uint32_t tmp[AGB_MAXANCHOR]; int nt = collect_runs(b, part, A, tmp, AGB_MAXANCHOR);
+				uint32_t tmp[AGB_MAXANCHOR]; int tp[AGB_MAXANCHOR], nt = collect_runs(b, part, A, tmp, tp, AGB_MAXANCHOR);
 				if (nt < d->k + 1 || ngot + d->k + 1 > AGB_MAXANCHOR) ok = 0;
-				else { memcpy(got + ngot, tmp, sizeof(uint32_t) * (size_t)(d->k + 1)); ngot += d->k + 1; }
+				else { memcpy(got + ngot, tmp, sizeof(uint32_t) * (size_t)(d->k + 1)); memcpy(pos + ngot, tp, sizeof(int) * (size_t)(d->k + 1)); ngot += d->k + 1; }
 			}
 		} else {                             /* single pattern or a;b (all must match): the part richest in runs */
 			int best = -1;
 			for (part = 1; part <= b->nparts; part++) {
-				uint32_t tmp[AGB_MAXANCHOR]; int nt = collect_runs(b, part, A, tmp, AGB_MAXANCHOR);
-				if (nt > best) { best = nt; memcpy(got, tmp, sizeof(uint32_t) * (size_t)nt); }
+				uint32_t tmp[AGB_MAXANCHOR]; int tp[AGB_MAXANCHOR], nt = collect_runs(b, part, A, tmp, tp, AGB_MAXANCHOR);
+				if (nt > best) { best = nt; memcpy(got, tmp, sizeof(uint32_t) * (size_t)nt); memcpy(pos, tp, sizeof(int) * (size_t)nt); }
 			}
 			if (best < d->k + 1) ok = 0; else ngot = d->k + 1;
 		}
 		if (!ok) continue;
 		d->plan = AGB_PLAN_ANCHORS; d->n_anchors = ngot; d->anchor_len = A;
 		d->anchor_mask = (A == 4) ? 0xFFFFFFFFu : (A == 3 ? 0x00FFFFFFu : 0x0000FFFFu);
+		/* case folding: the SAME 0x20 is OR-ed into every byte of the text words and of the anchors (a window
+		 * is cut from two words at any byte offset, so the fold must not depend on the byte lane).  Both
+		 * sides are folded alike, so this only widens the filter ('@' and '`' fall together, etc.). */
 		d->anchor_fold = 0;
 		if (o->nocase || fold_all)
 			for (p = 0; p < ngot; p++) {
 				int t;
-				for (t = 0; t < A; t++) if (is_alpha((int)(got[p] >> (8 * t) & 0xFF))) d->anchor_fold |= 0x20u << (8 * t);
+				for (t = 0; t < A; t++) if (is_alpha((int)(got[p] >> (8 * t) & 0xFF))) d->anchor_fold = 0x20202020u;
 			}
-		/* one fold mask for all anchors, OR-ed into text windows and anchors alike: a superset filter */
 		for (p = 0; p < ngot; p++) d->anchor[p] = (got[p] | d->anchor_fold) & d->anchor_mask;
+		/* stage 1.5: a hit of anchor i at text offset t can only belong to a match inside
+		 * [t - off_i - k, t + pat_len - off_i + k) when the pattern is a single part without '#' */
+		d->pat_len = d->M - d->L - 1;
+		for (p = 0; p < ngot; p++) d->anchor_off[p] = pos[p] - (d->L + 2);
+		d->refine = (b->nparts == 1 && !b->and_mode && !b->or_seen && d->wildmask == 0) ? 1 : 0;
 		return;
 	}
 }

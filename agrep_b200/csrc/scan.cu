@@ -31,6 +31,7 @@
 #include <mutex>
 #include <atomic>
 #include <algorithm>
+#include <thread>
 
 /* ------------------------------------------------------------------------------------------------ */
 static thread_local char g_err[512];
@@ -50,90 +51,135 @@ extern "C" int agb_set_device(int dev) { CUDA_TRY(cudaSetDevice(dev)); return AG
  * stage 1: anchor front-end
  * ============================================================================================== */
 #define FRONT_THREADS 256
-#define FRONT_UNROLL  4          /* 16-byte loads in flight per thread */
+#define FRONT_CH      4                                   /* 16-byte chunks per thread and stage              */
+#define FRONT_STAGE_CHUNKS (FRONT_THREADS * FRONT_CH)     /* 1024 chunks = 16 KiB = 32 bitmap words per stage */
+#define FRONT_STAGE_BYTES  (FRONT_STAGE_CHUNKS * 16)
+#define FRONT_SLOT_BYTES   (FRONT_STAGE_BYTES + 16)       /* + the 16 bytes that follow: the last chunk's windows look 3 bytes ahead */
+#define FRONT_NST     4                                   /* stages in flight per CTA (64 KiB), 3 CTAs per SM  */
+#define FRONT_CTAS_PER_SM 3
+#define FRONT_WORDS_PER_STAGE (FRONT_STAGE_CHUNKS / 32)
 
 struct FrontParams {
-	const uint4 *text;           /* 16-byte aligned */
+	const uint8_t *text;         /* 16-byte aligned */
 	uint32_t    *bitmap;         /* one word per 32 chunks */
 	uint64_t     n;              /* bytes */
 	uint64_t     n_chunks;       /* ceil(n/16) */
-	uint64_t     n_words;        /* ceil(n_chunks/32) */
+	uint64_t     readable;       /* bytes that may be read from text: 16 * n_chunks (+16 when the caller's slack allows) */
+	uint64_t     stage_begin, stage_end;   /* this launch covers stages [stage_begin, stage_end) of 1024 chunks each */
 	uint32_t     fold, amask;
+	uint32_t     one, scale;     /* 1 (kept opaque so the first Horner step stays an IMAD) and 256^(4-anchor_len) */
 	uint32_t     anchor[AGB_MAXANCHOR];
+	uint32_t     coef[AGB_MAXANCHOR];   /* prod_i (x - anchor[i]) mod 2^32, low order first, leading 1 implied */
 };
 
-__device__ __forceinline__ uint4 ld_stream16(const uint4 *p)
+/* ---- bulk-async copy (TMA, SASS UBLKCP) + mbarrier plumbing, shared::cta addressing ---- */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, int count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(b)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(b)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *b)
 {
-	uint4 v;
-	asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];"
-	             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-	return v;
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity)
+{
+	asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@!p bra WAIT_%=;\n}"
+	             :: "r"(smem_u32(b)), "r"(parity) : "memory");
 }
 
-/* does any window of the word pair (lo = bytes 0..3, hi = following word) equal an anchor?
- * windows start at byte 0,1,2,3 of lo.  NA anchors live in the constant bank (kernel parameters). */
-template <int NA, bool MASKED>
-__device__ __forceinline__ uint32_t windows_min(uint32_t lo, uint32_t hi, const FrontParams &P, uint32_t acc)
+/* The 4 windows that start in word `lo` (bytes 0..3; `hi` = the following word) against the NA anchors.
+ * Result: acc stays non-zero unless some window equals some anchor.
+ *
+ * POLY: f(w) = prod_i (w - A_i) mod 2^32, evaluated by Horner -- NA IMADs on the FMA pipe per window and
+ * half a VIMNMX3 on the ALU pipe, instead of NA compare-class ALU ops.  w == A_i  =>  f(w) == 0 exactly
+ * (ring identity), so the filter never loses a match; f(w) == 0 without an equal factor needs the 2-adic
+ * valuations of the NA differences to add up to 32, which front_launch() rules out up front (it falls back
+ * to the compare form when anchors share low-order bytes).  Anchors shorter than 4 bytes: f is scaled by
+ * 256^(4-len), which zeroes exactly when the low len bytes agree.
+ * !POLY: unsigned min of the differences (VIADDMNMX), one ALU op per window and anchor. */
+template <int NA, bool MASKED, bool POLY>
+__device__ __forceinline__ uint32_t windows_test(uint32_t lo, uint32_t hi, const FrontParams &P, uint32_t acc)
 {
-	uint32_t w0 = lo, w1 = __funnelshift_r(lo, hi, 8), w2 = __funnelshift_r(lo, hi, 16), w3 = __funnelshift_r(lo, hi, 24);
-	if (MASKED) { w0 &= P.amask; w1 &= P.amask; w2 &= P.amask; w3 &= P.amask; }
+	uint32_t w[4] = { lo, __funnelshift_r(lo, hi, 8), __funnelshift_r(lo, hi, 16), __funnelshift_r(lo, hi, 24) };
+	if (POLY) {
+		uint32_t f[4];
 #pragma unroll
-	for (int a = 0; a < NA; a++) {
-		/* unsigned min of differences is 0 iff some window equals some anchor (DPX min3: VIMNMX3) */
-		uint32_t A = P.anchor[a];
-		acc = __vimin3_u32(acc, w0 - A, w1 - A);
-		acc = __vimin3_u32(acc, w2 - A, w3 - A);
+		for (int t = 0; t < 4; t++) {
+			uint32_t r = w[t] * P.one + P.coef[NA - 1];
+#pragma unroll
+			for (int i = NA - 2; i >= 0; i--) r = r * w[t] + P.coef[i];
+			f[t] = MASKED ? r * P.scale : r;
+		}
+		acc = __vimin3_u32(acc, f[0], f[1]);
+		acc = __vimin3_u32(acc, f[2], f[3]);
+	} else {
+		if (MASKED) { w[0] &= P.amask; w[1] &= P.amask; w[2] &= P.amask; w[3] &= P.amask; }
+#pragma unroll
+		for (int a = 0; a < NA; a++) {
+			uint32_t A = P.anchor[a];
+			acc = __vimin3_u32(acc, w[0] - A, w[1] - A);
+			acc = __vimin3_u32(acc, w[2] - A, w[3] - A);
+		}
 	}
 	return acc;
 }
 
-template <int NA, bool MASKED, bool FOLD>
-__global__ void __launch_bounds__(FRONT_THREADS)
+/* Persistent CTAs.  Thread 0 keeps FRONT_NST bulk copies of 16 KiB (+16 B) in flight into a shared-memory
+ * ring, each completing on its own mbarrier; all 256 threads take 4 chunks per stage from shared memory
+ * (LDS.128, conflict-free: a warp reads 512 consecutive bytes), test the 16 windows of each chunk and ballot
+ * the 32 verdicts of a warp into one bitmap word.  Every text byte crosses HBM->SM once. */
+template <int NA, bool MASKED, bool FOLD, bool POLY>
+__global__ void __launch_bounds__(FRONT_THREADS, FRONT_CTAS_PER_SM)
 k_front(const FrontParams P)
 {
-	const uint32_t lane = threadIdx.x & 31;
-	const uint64_t warp = ((uint64_t)blockIdx.x * FRONT_THREADS + threadIdx.x) >> 5;
-	const uint64_t nwarps = ((uint64_t)gridDim.x * FRONT_THREADS) >> 5;
-	/* each warp takes groups of FRONT_UNROLL consecutive bitmap words (= FRONT_UNROLL * 512 bytes) */
-	const uint64_t n_groups = (P.n_words + FRONT_UNROLL - 1) / FRONT_UNROLL;
-	for (uint64_t g = warp; g < n_groups; g += nwarps) {
-		const uint64_t w0 = g * FRONT_UNROLL;
-		uint4 v[FRONT_UNROLL + 1];
+	extern __shared__ __align__(128) uint8_t s_ring[];
+	__shared__ uint64_t s_bar[FRONT_NST];
+	const uint32_t tid = threadIdx.x, lane = tid & 31;
+	if (tid == 0) {
+		for (int i = 0; i < FRONT_NST; i++) mbar_init(&s_bar[i], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	auto issue = [&](uint64_t it) {
+		const uint64_t sg = P.stage_begin + blockIdx.x + it * gridDim.x;
+		if (sg >= P.stage_end) return;
+		const uint32_t slot = (uint32_t)(it % FRONT_NST);
+		const uint64_t off = sg * FRONT_STAGE_BYTES, avail = P.readable - off;
+		const uint32_t bytes = (uint32_t)(avail < FRONT_SLOT_BYTES ? (avail & ~15ull) : FRONT_SLOT_BYTES);
+		mbar_expect_tx(&s_bar[slot], bytes);
+		bulk_g2s(s_ring + slot * FRONT_SLOT_BYTES, P.text + off, bytes, &s_bar[slot]);
+	};
+	if (tid == 0) for (int i = 0; i < FRONT_NST; i++) issue(i);
+	for (uint64_t it = 0;; it++) {
+		const uint64_t sg = P.stage_begin + blockIdx.x + it * gridDim.x;
+		if (sg >= P.stage_end) break;
+		const uint32_t slot = (uint32_t)(it % FRONT_NST);
+		mbar_wait(&s_bar[slot], (uint32_t)((it / FRONT_NST) & 1));
+		const uint8_t *st = s_ring + slot * FRONT_SLOT_BYTES;
 #pragma unroll
-		for (int u = 0; u < FRONT_UNROLL; u++) {
-			uint64_t c = (w0 + u) * 32 + lane;
-			v[u] = (c < P.n_chunks) ? ld_stream16(P.text + c) : make_uint4(0, 0, 0, 0);
-		}
-		{   /* the word that follows this group: only its first 4 bytes are needed, by lane 31 of the last word */
-			uint64_t c = (w0 + FRONT_UNROLL) * 32;
-			uint32_t nx = 0;
-			if (lane == 0 && c < P.n_chunks) nx = __ldg(reinterpret_cast<const uint32_t *>(P.text + c));
-			v[FRONT_UNROLL] = make_uint4(nx, 0, 0, 0);
-		}
-#pragma unroll
-		for (int u = 0; u < FRONT_UNROLL; u++) {
-			if (w0 + u >= P.n_words) break;
-			/* lane L needs the first word of the next chunk: lane L+1 of this vector, or lane 0 of the next one */
-			uint32_t give = (lane == 0) ? v[u + 1].x : v[u].x;
-			uint32_t x4 = __shfl_sync(0xffffffffu, give, (lane + 1) & 31);
-			uint32_t x0 = v[u].x, x1 = v[u].y, x2 = v[u].z, x3 = v[u].w;
-			if (FOLD) { x0 |= P.fold; x1 |= P.fold; x2 |= P.fold; x3 |= P.fold; x4 |= P.fold; }
+		for (int c = 0; c < FRONT_CH; c++) {
+			const uint32_t idx = c * FRONT_THREADS + tid;
+			uint4 v = *reinterpret_cast<const uint4 *>(st + idx * 16);
+			uint32_t x4 = *reinterpret_cast<const uint32_t *>(st + idx * 16 + 16);
+			if (FOLD) { v.x |= P.fold; v.y |= P.fold; v.z |= P.fold; v.w |= P.fold; x4 |= P.fold; }
 			uint32_t acc = 0xffffffffu;
-			acc = windows_min<NA, MASKED>(x0, x1, P, acc);
-			acc = windows_min<NA, MASKED>(x1, x2, P, acc);
-			acc = windows_min<NA, MASKED>(x2, x3, P, acc);
-			acc = windows_min<NA, MASKED>(x3, x4, P, acc);
-			uint64_t c = (w0 + u) * 32 + lane;
-			/* the last chunks are always passed on: a match may run into the delimiter appended at EOF (bitap.c:161-165) */
-			bool flag = (c < P.n_chunks) && (acc == 0 || c + 2 >= P.n_chunks);
-			uint32_t word = __ballot_sync(0xffffffffu, flag);
-			if (lane == 0) P.bitmap[w0 + u] = word;
+			acc = windows_test<NA, MASKED, POLY>(v.x, v.y, P, acc);
+			acc = windows_test<NA, MASKED, POLY>(v.y, v.z, P, acc);
+			acc = windows_test<NA, MASKED, POLY>(v.z, v.w, P, acc);
+			acc = windows_test<NA, MASKED, POLY>(v.w, x4, P, acc);
+			const uint64_t chunk = sg * FRONT_STAGE_CHUNKS + idx;
+			/* the last chunks are always passed on: a match may run into the delimiter appended at EOF (bitap.c:161-165),
+			 * and their look-ahead bytes may not exist */
+			const bool flag = (chunk < P.n_chunks) && (acc == 0 || chunk + 2 >= P.n_chunks);
+			const uint32_t word = __ballot_sync(0xffffffffu, flag);
+			if (lane == 0 && chunk < P.n_chunks) P.bitmap[chunk >> 5] = word;
 		}
+		__syncthreads();                       /* everyone is done reading this slot */
+		if (tid == 0) issue(it + FRONT_NST);   /* refill it with the stage FRONT_NST iterations ahead */
 	}
 }
-
-/* with FOLD the fold mask must not be applied twice to the shifted-in word: windows are built from
- * already folded words, so x4 is folded above and funnel shifts commute with the byte-wise OR. */
 
 /* ================================================================================================
  * stage 2: records
@@ -365,6 +411,96 @@ k_records(const RecParams P)
 	}
 }
 
+/* ================================================================================================
+ * stage 1.5: local verification of anchor hits
+ *
+ * Stage 1 passes every chunk in which an anchor starts; for a pattern made of common words that is a few
+ * percent of all chunks, almost none of which belong to a match.  A match that uses the anchor occurrence at
+ * text offset t aligns the pat_len pattern positions to text inside [t - off - k, t + pat_len - off + k), so
+ * running the SAME recurrence over just that window (all rows started at Init[0], whose separator bit is the
+ * always-on start state; no record logic, which can only remove bits) decides whether the hit can matter.
+ * Chunks none of whose hits survive lose their bitmap bit.  Warps compact their 1024 chunks into a queue first,
+ * so all 32 lanes verify candidates.
+ * ============================================================================================== */
+#define REFINE_THREADS 128
+struct RefineParams {
+	const uint8_t *text; uint32_t *bitmap; uint64_t n, n_chunks, n_words;
+	const agb_desc *desc;
+	uint32_t fold, amask; int na;
+	uint32_t anchor[AGB_MAXANCHOR]; int32_t off[AGB_MAXANCHOR];
+};
+
+template <typename T, int NR, bool COSTS>
+__global__ void __launch_bounds__(REFINE_THREADS)
+k_refine(const RefineParams P)
+{
+	__shared__ T s_mask[257];
+	__shared__ uint8_t s_delim[2 * AGB_MAXDELIM + 2];
+	__shared__ uint16_t s_queue[REFINE_THREADS / 32][1024];
+	__shared__ uint32_t s_keep[REFINE_THREADS / 32][32];
+	const agb_desc *D = P.desc;
+	for (int i = threadIdx.x; i < 256; i += REFINE_THREADS) s_mask[i] = (T)D->mask[i];
+	if (threadIdx.x == 0) s_mask[256] = 0;                   /* byte "256": outside the text, matches nothing */
+	if (threadIdx.x < 2 * AGB_MAXDELIM + 2) s_delim[threadIdx.x] = D->delim[threadIdx.x];
+	DevConsts<T> C;
+	C.init1 = (T)D->init1; C.noerr = (T)D->noerr; C.endpos = (T)D->endpos; C.dendpos = (T)D->dendpos;
+	C.L = D->L; C.k = D->k; C.and_mode = D->and_mode; C.inverse = D->inverse; C.kind = D->delim_kind;
+	C.ci = D->cost_i; C.cs = D->cost_s; C.cd = D->cost_d;
+	const T init0 = (T)D->init0;
+	const int pat_len = D->pat_len, k = D->k;
+	__syncthreads();
+	const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const uint64_t warp = ((uint64_t)blockIdx.x * REFINE_THREADS + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * REFINE_THREADS) >> 5;
+	const uint64_t n_groups = (P.n_words + 31) / 32;
+	Reader R; R.init(P.text, P.n, s_delim, C.L);
+	for (uint64_t g = warp; g < n_groups; g += nwarps) {
+		const uint64_t w = g * 32 + lane;
+		const uint32_t word = (w < P.n_words) ? P.bitmap[w] : 0u;
+		if (__ballot_sync(0xffffffffu, word != 0) == 0) continue;
+		/* compact the flagged chunks of these 32 words into the warp's queue */
+		uint32_t cnt = __popc(word), pre = cnt;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= (uint32_t)o) pre += v; }
+		const uint32_t total = __shfl_sync(0xffffffffu, pre, 31);
+		pre -= cnt;
+		for (uint32_t b = word; b; b &= b - 1) s_queue[wib][pre++] = (uint16_t)(lane * 32 + (__ffs(b) - 1));
+		s_keep[wib][lane] = 0;
+		__syncwarp();
+		for (uint32_t qi = lane; qi < total; qi += 32) {
+			const uint32_t cidx = s_queue[wib][qi];
+			const int64_t chunk = (int64_t)(g * 1024 + cidx), base = chunk * 16;
+			bool keep = (uint64_t)chunk + 2 >= P.n_chunks;      /* the EOF chunks stay (appended delimiter, bitap.c:161-165) */
+			if (!keep) {
+				/* which windows of this chunk hit which anchor?  (exactly stage 1's test, exact compare) */
+				const uint4 v = __ldg(reinterpret_cast<const uint4 *>(P.text) + chunk);
+				const uint32_t nx = __ldg(reinterpret_cast<const uint32_t *>(P.text) + (chunk + 1) * 4);
+				uint32_t x[5] = { v.x | P.fold, v.y | P.fold, v.z | P.fold, v.w | P.fold, nx | P.fold };
+				for (int s = 0; s < 16 && !keep; s++) {
+					const uint32_t wv = __funnelshift_r(x[s >> 2], x[(s >> 2) + 1], (s & 3) * 8) & P.amask;
+					for (int a = 0; a < P.na && !keep; a++) {
+						if (wv != P.anchor[a]) continue;
+						const int64_t t = base + s, ws = t - P.off[a] - k, we = t + pat_len - P.off[a] + k;
+						T S[NR];
+#pragma unroll
+						for (int r = 0; r < NR; r++) S[r] = init0;
+						T seen = 0;
+						for (int64_t q = ws; q < we; q++) {
+							rows_step<T, NR, COSTS>(S, s_mask[R.get(q)], C);
+							seen |= S[NR - 1];
+						}
+						keep = (seen & C.endpos) != 0;
+					}
+				}
+			}
+			if (keep) atomicOr(&s_keep[wib][cidx >> 5], 1u << (cidx & 31));
+		}
+		__syncwarp();
+		const uint32_t nw = s_keep[wib][lane];
+		if (w < P.n_words && nw != word) P.bitmap[w] = nw;
+		__syncwarp();
+	}
+}
+
 /* exclusive scan of the per-tile counts (one block; the array has n/64KiB entries) */
 __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *counts, uint64_t *offsets, uint64_t n_tiles)
 {
@@ -393,14 +529,23 @@ static const char h_vocab[] = AGB_VOCAB_STR;
 
 struct CorpusParams { agb_corpus_spec s; int needle_len; };
 
-__global__ void __launch_bounds__(128) k_corpus(uint8_t *out, uint64_t n_pages, const CorpusParams P)
+#define CORPUS_THREADS 32
+#define CORPUS_STRIDE  (AGB_PAGE + 4)     /* +1 word: the 32 generator threads hit different banks */
+__global__ void __launch_bounds__(CORPUS_THREADS) k_corpus(uint8_t *out, uint64_t n_pages, const CorpusParams P)
 {
-	/* one thread per page keeps the generator identical to the host loop; pages are staged in
-	 * shared memory? no: 4 KiB per thread is too much -- write straight to HBM (generation is not timed) */
-	uint64_t pg = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (pg >= n_pages) return;
-	agb_corpus_page(out + pg * AGB_PAGE, P.s.seed, P.s.first_page + pg, c_vocab, c_woff,
-	                P.s.paragraphs, P.s.needle_every, P.s.needle, P.needle_len, P.s.needle_maxedits);
+	/* one thread generates one 4 KiB page (the generator is inherently sequential) into shared memory,
+	 * then the warp writes the 32 pages out with coalesced 128-byte stores */
+	extern __shared__ __align__(16) uint8_t s_pages[];
+	const uint64_t pg0 = (uint64_t)blockIdx.x * CORPUS_THREADS, pg = pg0 + threadIdx.x;
+	if (pg < n_pages)
+		agb_corpus_page(s_pages + threadIdx.x * CORPUS_STRIDE, P.s.seed, P.s.first_page + pg, c_vocab, c_woff,
+		                P.s.paragraphs, P.s.needle_every, P.s.needle, P.needle_len, P.s.needle_maxedits);
+	__syncwarp();
+	for (int q = 0; q < CORPUS_THREADS && pg0 + q < n_pages; q++) {
+		const uint32_t *src = reinterpret_cast<const uint32_t *>(s_pages + q * CORPUS_STRIDE);
+		uint32_t *dst = reinterpret_cast<uint32_t *>(out + (pg0 + q) * AGB_PAGE);
+		for (int j = threadIdx.x; j < AGB_PAGE / 4; j += CORPUS_THREADS) dst[j] = src[j];
+	}
 }
 
 static int corpus_check(const agb_corpus_spec *s, uint16_t *woff)
@@ -419,7 +564,9 @@ extern "C" int agb_corpus_fill_device(const agb_corpus_spec *s, void *d_text, vo
 	CorpusParams P; P.s = *s; P.s.needle[63] = 0; P.needle_len = (int)strlen(P.s.needle);
 	uint64_t n_pages = s->n_bytes / AGB_PAGE;
 	if (n_pages) {
-		k_corpus<<<(unsigned)((n_pages + 127) / 128), 128, 0, st>>>((uint8_t *)d_text, n_pages, P);
+		const int smem = CORPUS_THREADS * CORPUS_STRIDE;
+		CUDA_TRY(cudaFuncSetAttribute(k_corpus, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		k_corpus<<<(unsigned)((n_pages + CORPUS_THREADS - 1) / CORPUS_THREADS), CORPUS_THREADS, smem, st>>>((uint8_t *)d_text, n_pages, P);
 		g_launches++;
 		CUDA_TRY(cudaGetLastError());
 	}
@@ -440,14 +587,23 @@ extern "C" int agb_corpus_fill_host(const agb_corpus_spec *s, void *h_text)
 /* ================================================================================================
  * host side of the scan
  * ============================================================================================== */
+#define H2D_SLICE   (64ull << 20)      /* bytes per H2D slice of agb_scan_host; a multiple of the 16 KiB stage */
+#define STAGE_BUFS  3
+
 struct Workspace {               /* grow-only device scratch, one per device */
 	uint32_t *bitmap = nullptr; size_t bitmap_bytes = 0;
 	uint32_t *tile_counts = nullptr; uint64_t *tile_offsets = nullptr; size_t tiles = 0;
-	unsigned long long *totals = nullptr;          /* 12 counters */
+	unsigned long long *totals = nullptr;          /* 16 counters */
 	unsigned long long *h_totals = nullptr;        /* pinned */
 	agb_desc *d_desc = nullptr; agb_desc h_desc_copy; bool desc_valid = false;
 	cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
 	int sm_count = 0;
+	/* agb_scan_host: device copy of the text, record buffer, copy stream, pinned staging for pageable sources */
+	uint8_t *h2d_text = nullptr; size_t h2d_cap = 0;
+	agb_record *h2d_rec = nullptr; size_t h2d_rec_cap = 0;
+	cudaStream_t s_copy = nullptr, s_comp = nullptr;
+	cudaEvent_t ev_copy[STAGE_BUFS] = {nullptr, nullptr, nullptr};
+	uint8_t *stage[STAGE_BUFS] = {nullptr, nullptr, nullptr};
 };
 static Workspace g_ws[64];
 static std::mutex g_ws_mu;
@@ -463,7 +619,7 @@ static int ws_prepare(Workspace &W, uint64_t n)
 		CUDA_TRY(cudaDeviceGetAttribute(&W.sm_count, cudaDevAttrMultiProcessorCount, dev));
 	}
 	uint64_t n_chunks = (n + 15) / 16, n_words = (n_chunks + 31) / 32, tiles = (n_words + REC_THREADS - 1) / REC_THREADS;
-	size_t bb = (size_t)(n_words + FRONT_UNROLL) * 4;
+	size_t bb = (size_t)(n_words + FRONT_WORDS_PER_STAGE) * 4;
 	if (bb > W.bitmap_bytes) {
 		if (W.bitmap) cudaFree(W.bitmap);
 		W.bitmap = nullptr; W.bitmap_bytes = 0;
@@ -480,30 +636,92 @@ static int ws_prepare(Workspace &W, uint64_t n)
 	return AGB_OK;
 }
 
-template <int NA>
-static void launch_front_na(const FrontParams &P, bool masked, bool fold, unsigned grid, cudaStream_t st)
+static int ws_upload_desc(Workspace &W, const agb_desc &d, cudaStream_t st)
 {
-	if (masked) { if (fold) k_front<NA, true, true><<<grid, FRONT_THREADS, 0, st>>>(P); else k_front<NA, true, false><<<grid, FRONT_THREADS, 0, st>>>(P); }
-	else        { if (fold) k_front<NA, false, true><<<grid, FRONT_THREADS, 0, st>>>(P); else k_front<NA, false, false><<<grid, FRONT_THREADS, 0, st>>>(P); }
+	if (!W.desc_valid || memcmp(&W.h_desc_copy, &d, sizeof d) != 0) {
+		CUDA_TRY(cudaMemcpyAsync(W.d_desc, &d, sizeof d, cudaMemcpyHostToDevice, st));
+		CUDA_TRY(cudaStreamSynchronize(st));     /* &d may be on the caller's stack */
+		W.h_desc_copy = d; W.desc_valid = true;
+	}
+	return AGB_OK;
 }
 
-static int launch_front(const agb_desc &d, const FrontParams &P, unsigned grid, cudaStream_t st)
+#define FRONT_SMEM (FRONT_NST * FRONT_SLOT_BYTES)
+template <int NA, bool MASKED, bool FOLD, bool POLY>
+static void launch_front_one(const FrontParams &P, unsigned grid, cudaStream_t st)
 {
-	bool masked = d.anchor_mask != 0xFFFFFFFFu, fold = d.anchor_fold != 0;
-	switch (d.n_anchors) {
-	case 1: launch_front_na<1>(P, masked, fold, grid, st); break;
-	case 2: launch_front_na<2>(P, masked, fold, grid, st); break;
-	case 3: launch_front_na<3>(P, masked, fold, grid, st); break;
-	case 4: launch_front_na<4>(P, masked, fold, grid, st); break;
-	case 5: launch_front_na<5>(P, masked, fold, grid, st); break;
-	case 6: launch_front_na<6>(P, masked, fold, grid, st); break;
-	case 7: launch_front_na<7>(P, masked, fold, grid, st); break;
-	case 8: launch_front_na<8>(P, masked, fold, grid, st); break;
-	case 9: launch_front_na<9>(P, masked, fold, grid, st); break;
-	default: return -1;
+	static bool configured[64] = {false};
+	int dev = 0; cudaGetDevice(&dev);
+	if (!configured[dev & 63]) {
+		cudaFuncSetAttribute(k_front<NA, MASKED, FOLD, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, FRONT_SMEM);
+		configured[dev & 63] = true;
 	}
+	k_front<NA, MASKED, FOLD, POLY><<<grid, FRONT_THREADS, FRONT_SMEM, st>>>(P);
+}
+template <int NA, bool POLY>
+static void launch_front_na(const FrontParams &P, bool masked, bool fold, unsigned grid, cudaStream_t st)
+{
+	if (masked) { if (fold) launch_front_one<NA, true, true, POLY>(P, grid, st); else launch_front_one<NA, true, false, POLY>(P, grid, st); }
+	else        { if (fold) launch_front_one<NA, false, true, POLY>(P, grid, st); else launch_front_one<NA, false, false, POLY>(P, grid, st); }
+}
+
+/* coefficients of prod_i (x - a_i) mod 2^32 and the false-positive guard of the polynomial form:
+ * a zero product without a zero factor needs sum_i v2(w - a_i) >= bits; with t = the largest v2(a_i - a_j)
+ * at most one factor can exceed t, so w must agree with an anchor in its low bits - (na-1)*t bits.  We ask
+ * for at least 20 agreeing bits (a 2.5-byte accidental match) or use the compare form instead. */
+static bool poly_setup(const uint32_t *a, int na, int bits, uint32_t *coef)
+{
+	uint32_t c[AGB_MAXANCHOR + 1]; int deg = 0, t = 0;
+	memset(c, 0, sizeof c); c[0] = 1;
+	for (int i = 0; i < na; i++) {
+		uint32_t m = 0u - a[i];
+		for (int j = deg + 1; j >= 1; j--) c[j] = c[j - 1] + c[j] * m;
+		c[0] = c[0] * m; deg++;
+		for (int j = 0; j < i; j++) { uint32_t dd = a[i] - a[j]; int v = dd ? __builtin_ctz(dd) : 32; if (v > t) t = v; }
+	}
+	for (int i = 0; i < na; i++) coef[i] = c[i];
+	return bits - (na - 1) * t >= 20;
+}
+
+static bool front_usable(const agb_desc &d) { return d.plan == AGB_PLAN_ANCHORS && d.n_anchors >= 1 && d.n_anchors <= 9; }
+
+/* stage 1 over bitmap words [word_begin, word_end) of a text of n bytes; word_begin must be a multiple of 32
+ * (a stage is 32 words).  slack16: 16 more bytes after the last chunk are readable (true for our own buffers). */
+static int front_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n,
+                        uint64_t word_begin, uint64_t word_end, bool slack16, cudaStream_t st)
+{
+	const uint64_t n_chunks = (n + 15) / 16, n_words = (n_chunks + 31) / 32;
+	if (word_end > n_words) word_end = n_words;
+	if (word_begin >= word_end) return AGB_OK;
+	FrontParams F; memset(&F, 0, sizeof F);
+	F.text = (const uint8_t *)d_text; F.bitmap = W.bitmap; F.n = n; F.n_chunks = n_chunks;
+	F.readable = n_chunks * 16 + (slack16 ? 16 : 0);
+	F.stage_begin = word_begin / FRONT_WORDS_PER_STAGE;
+	F.stage_end = (word_end + FRONT_WORDS_PER_STAGE - 1) / FRONT_WORDS_PER_STAGE;
+	F.fold = d.anchor_fold; F.amask = d.anchor_mask;
+	const uint64_t stages = F.stage_end - F.stage_begin;
+	unsigned grid = (unsigned)std::min<uint64_t>(stages, (uint64_t)W.sm_count * FRONT_CTAS_PER_SM);
+	if (!grid) grid = 1;
+	bool masked = d.anchor_mask != 0xFFFFFFFFu, fold = d.anchor_fold != 0;
+	/* identical anchors (e.g. from "abababab") are tested once */
+	int na = 0;
+	for (int i = 0; i < d.n_anchors; i++) {
+		bool dup = false;
+		for (int j = 0; j < na; j++) if (F.anchor[j] == d.anchor[i]) dup = true;
+		if (!dup) F.anchor[na++] = d.anchor[i];
+	}
+	F.one = 1; F.scale = 1;
+	for (int i = d.anchor_len; i < 4; i++) F.scale <<= 8;
+	const bool poly = poly_setup(F.anchor, na, 8 * d.anchor_len, F.coef);
+#define FRONT_CASE(N) case N: if (poly) launch_front_na<N, true>(F, masked, fold, grid, st); else launch_front_na<N, false>(F, masked, fold, grid, st); break;
+	switch (na) {
+	FRONT_CASE(1) FRONT_CASE(2) FRONT_CASE(3) FRONT_CASE(4) FRONT_CASE(5) FRONT_CASE(6) FRONT_CASE(7) FRONT_CASE(8) FRONT_CASE(9)
+	default: return AGB_ERR_ARG;
+	}
+#undef FRONT_CASE
 	g_launches++;
-	return 0;
+	CUDA_TRY(cudaGetLastError());
+	return AGB_OK;
 }
 
 template <typename T, bool COSTS>
@@ -533,6 +751,78 @@ static int launch_records(const agb_desc &d, const RecParams &P, unsigned grid, 
 	return narrow ? launch_records_t<uint32_t, false>(d.nrows, P, grid, st) : launch_records_t<uint64_t, false>(d.nrows, P, grid, st);
 }
 
+template <typename T, bool COSTS>
+static int launch_refine_t(int nrows, const RefineParams &P, unsigned grid, cudaStream_t st)
+{
+	switch (nrows) {
+	case 1: k_refine<T, 1, COSTS><<<grid, REFINE_THREADS, 0, st>>>(P); break;
+	case 2: k_refine<T, 2, COSTS><<<grid, REFINE_THREADS, 0, st>>>(P); break;
+	case 3: k_refine<T, 3, COSTS><<<grid, REFINE_THREADS, 0, st>>>(P); break;
+	case 4: k_refine<T, 4, COSTS><<<grid, REFINE_THREADS, 0, st>>>(P); break;
+	case 5: k_refine<T, 5, COSTS><<<grid, REFINE_THREADS, 0, st>>>(P); break;
+	case 6: k_refine<T, 6, COSTS><<<grid, REFINE_THREADS, 0, st>>>(P); break;
+	case 7: k_refine<T, 7, COSTS><<<grid, REFINE_THREADS, 0, st>>>(P); break;
+	case 8: k_refine<T, 8, COSTS><<<grid, REFINE_THREADS, 0, st>>>(P); break;
+	case 9: k_refine<T, 9, COSTS><<<grid, REFINE_THREADS, 0, st>>>(P); break;
+	default: return -1;
+	}
+	g_launches++;
+	return 0;
+}
+
+/* stage 1.5 over the whole bitmap (only when the plan allows a purely local check) */
+static int refine_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, cudaStream_t st)
+{
+	if (!front_usable(d) || !d.refine || n == 0) return AGB_OK;
+	const uint64_t n_chunks = (n + 15) / 16, n_words = (n_chunks + 31) / 32;
+	RefineParams P; memset(&P, 0, sizeof P);
+	P.text = (const uint8_t *)d_text; P.bitmap = W.bitmap; P.n = n; P.n_chunks = n_chunks; P.n_words = n_words; P.desc = W.d_desc;
+	P.fold = d.anchor_fold; P.amask = d.anchor_mask; P.na = d.n_anchors;
+	for (int i = 0; i < d.n_anchors; i++) { P.anchor[i] = d.anchor[i]; P.off[i] = d.anchor_off[i]; }
+	const uint64_t groups = (n_words + 31) / 32;
+	unsigned grid = (unsigned)std::min<uint64_t>((groups + 3) / 4, (uint64_t)W.sm_count * 16);
+	if (!grid) grid = 1;
+	const bool costs = d.engine == AGB_ENGINE_ASEARCH1, narrow = d.M <= 31;
+	int rc = costs ? (narrow ? launch_refine_t<uint32_t, true>(d.nrows, P, grid, st) : launch_refine_t<uint64_t, true>(d.nrows, P, grid, st))
+	               : (narrow ? launch_refine_t<uint32_t, false>(d.nrows, P, grid, st) : launch_refine_t<uint64_t, false>(d.nrows, P, grid, st));
+	if (rc) return AGB_ERR_ARG;
+	CUDA_TRY(cudaGetLastError());
+	return AGB_OK;
+}
+
+/* stage 2 (+ tile scan + emit pass when a list is wanted) over the whole text */
+static int records_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, bool use_front, int want,
+                          int want_level, agb_record *d_records, uint64_t capacity, cudaStream_t st)
+{
+	const uint64_t n_chunks = (n + 15) / 16, n_words = (n_chunks + 31) / 32, tiles = (n_words + REC_THREADS - 1) / REC_THREADS;
+	RecParams P; memset(&P, 0, sizeof P);
+	P.text = (const uint8_t *)d_text; P.bitmap = use_front ? W.bitmap : nullptr;
+	P.n = n; P.n_chunks = n_chunks; P.n_words = n_words; P.desc = W.d_desc;
+	P.tile_counts = W.tile_counts; P.tile_offsets = W.tile_offsets; P.records = d_records; P.capacity = capacity;
+	P.totals = W.totals; P.emit = 0; P.levels = (want & AGB_WANT_LEVELS) ? 1 : 0; P.want_level = want_level;
+	if (!tiles) return AGB_OK;
+	if (launch_records(d, P, (unsigned)tiles, st)) return AGB_ERR_ARG;
+	CUDA_TRY(cudaGetLastError());
+	if ((want & AGB_WANT_RECORDS) && capacity) {
+		k_scan_tiles<<<1, 1024, 0, st>>>(W.tile_counts, W.tile_offsets, tiles); g_launches++;
+		P.emit = 1;
+		if (launch_records(d, P, (unsigned)tiles, st)) return AGB_ERR_ARG;
+		CUDA_TRY(cudaGetLastError());
+	}
+	return AGB_OK;
+}
+
+static int fetch_result(Workspace &W, int want, uint64_t capacity, cudaStream_t st, agb_result *res)
+{
+	CUDA_TRY(cudaMemcpyAsync(W.h_totals, W.totals, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	res->n_matched = W.h_totals[0];
+	res->n_flagged = W.h_totals[1];
+	for (int i = 0; i <= AGB_MAXERR; i++) res->level_hist[i] = W.h_totals[2 + i];
+	res->n_records = (want & AGB_WANT_RECORDS) ? std::min<uint64_t>(res->n_matched, capacity) : 0;
+	return AGB_OK;
+}
+
 static int scan_device_impl(const agb_desc &d, const void *d_text, uint64_t n, int want, int want_level,
                             agb_record *d_records, uint64_t capacity, cudaStream_t st, agb_result *res)
 {
@@ -545,49 +835,16 @@ static int scan_device_impl(const agb_desc &d, const void *d_text, uint64_t n, i
 	std::lock_guard<std::mutex> lk(g_ws_mu);
 	Workspace &W = g_ws[dev];
 	int rc = ws_prepare(W, n); if (rc) return rc;
-	if (!W.desc_valid || memcmp(&W.h_desc_copy, &d, sizeof d) != 0) {
-		CUDA_TRY(cudaMemcpyAsync(W.d_desc, &d, sizeof d, cudaMemcpyHostToDevice, st));
-		CUDA_TRY(cudaStreamSynchronize(st));     /* &d may be on the caller's stack */
-		W.h_desc_copy = d; W.desc_valid = true;
-	}
-	const uint64_t n_chunks = (n + 15) / 16, n_words = (n_chunks + 31) / 32, tiles = (n_words + REC_THREADS - 1) / REC_THREADS;
+	rc = ws_upload_desc(W, d, st); if (rc) return rc;
 	CUDA_TRY(cudaMemsetAsync(W.totals, 0, 16 * sizeof(unsigned long long), st));
 	CUDA_TRY(cudaEventRecord(W.e0, st));
-	const bool use_front = d.plan == AGB_PLAN_ANCHORS && d.n_anchors >= 1 && d.n_anchors <= 9 && n_words > 0;
-	if (use_front) {
-		FrontParams F; memset(&F, 0, sizeof F);
-		F.text = (const uint4 *)d_text; F.bitmap = W.bitmap; F.n = n; F.n_chunks = n_chunks; F.n_words = n_words;
-		F.fold = d.anchor_fold; F.amask = d.anchor_mask;
-		for (int i = 0; i < d.n_anchors; i++) F.anchor[i] = d.anchor[i];
-		uint64_t groups = (n_words + FRONT_UNROLL - 1) / FRONT_UNROLL;
-		uint64_t want_blocks = (groups * 32 + FRONT_THREADS - 1) / FRONT_THREADS;
-		unsigned grid = (unsigned)std::min<uint64_t>(want_blocks, (uint64_t)W.sm_count * 8);
-		if (launch_front(d, F, grid ? grid : 1, st)) return AGB_ERR_ARG;
-		CUDA_TRY(cudaGetLastError());
-	}
+	const bool use_front = front_usable(d) && n > 0;
+	if (use_front) { rc = front_launch(d, W, d_text, n, 0, ~0ull, false, st); if (rc) return rc; }
 	CUDA_TRY(cudaEventRecord(W.e1, st));
-	RecParams P; memset(&P, 0, sizeof P);
-	P.text = (const uint8_t *)d_text; P.bitmap = use_front ? W.bitmap : nullptr;
-	P.n = n; P.n_chunks = n_chunks; P.n_words = n_words; P.desc = W.d_desc;
-	P.tile_counts = W.tile_counts; P.tile_offsets = W.tile_offsets; P.records = d_records; P.capacity = capacity;
-	P.totals = W.totals; P.emit = 0; P.levels = (want & AGB_WANT_LEVELS) ? 1 : 0; P.want_level = want_level;
-	if (tiles) {
-		if (launch_records(d, P, (unsigned)tiles, st)) return AGB_ERR_ARG;
-		CUDA_TRY(cudaGetLastError());
-		if ((want & AGB_WANT_RECORDS) && capacity) {
-			k_scan_tiles<<<1, 1024, 0, st>>>(W.tile_counts, W.tile_offsets, tiles); g_launches++;
-			P.emit = 1;
-			if (launch_records(d, P, (unsigned)tiles, st)) return AGB_ERR_ARG;
-			CUDA_TRY(cudaGetLastError());
-		}
-	}
+	if (use_front) { rc = refine_launch(d, W, d_text, n, st); if (rc) return rc; }
+	rc = records_launch(d, W, d_text, n, use_front, want, want_level, d_records, capacity, st); if (rc) return rc;
 	CUDA_TRY(cudaEventRecord(W.e2, st));
-	CUDA_TRY(cudaMemcpyAsync(W.h_totals, W.totals, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-	CUDA_TRY(cudaStreamSynchronize(st));
-	res->n_matched = W.h_totals[0];
-	res->n_flagged = W.h_totals[1];
-	for (int i = 0; i <= AGB_MAXERR; i++) res->level_hist[i] = W.h_totals[2 + i];
-	res->n_records = (want & AGB_WANT_RECORDS) ? std::min<uint64_t>(res->n_matched, capacity) : 0;
+	rc = fetch_result(W, want, capacity, st, res); if (rc) return rc;
 	CUDA_TRY(cudaEventElapsedTime(&res->ms_front, W.e0, W.e1));
 	CUDA_TRY(cudaEventElapsedTime(&res->ms_records, W.e1, W.e2));
 	return AGB_OK;
@@ -600,28 +857,95 @@ extern "C" int agb_scan_device(const agb_pattern *p, const void *d_text, uint64_
 	return scan_device_impl(p->d, d_text, n, want, -1, d_records, capacity, (cudaStream_t)stream, res);
 }
 
-/* host text: for now one staged copy + one scan per slice of at most SLICE bytes cut at record boundaries */
+static void par_memcpy(uint8_t *dst, const uint8_t *src, size_t len)
+{
+	const int T = 4; const size_t part = ((len + T - 1) / T + 4095) & ~(size_t)4095;
+	std::thread th[T]; int used = 0;
+	for (int t = 0; t < T; t++) {
+		size_t a = (size_t)t * part; if (a >= len) break;
+		size_t l = std::min(part, len - a);
+		th[used++] = std::thread([=] { memcpy(dst + a, src + a, l); });
+	}
+	for (int t = 0; t < used; t++) th[t].join();
+}
+
+/* Host text -> HBM -> scan: the replacement of the fill_buf()/read(2) loop (bitap.c:143,450-477).  The text is
+ * moved in 64 MiB slices on a copy stream (straight from the caller's memory when it is page-locked, else
+ * through a pinned ring filled by 4 host threads) while stage 1 runs on the slice that arrived before, so
+ * the scan hides behind PCIe; stage 2 runs once over the whole bitmap. */
 extern "C" int agb_scan_host(const agb_pattern *p, const void *h_text, uint64_t n, int want,
                              agb_record *records, uint64_t capacity, agb_result *res)
 {
 	if (!p || !res || (!h_text && n)) return AGB_ERR_ARG;
-	uint8_t *d_text = nullptr; agb_record *d_rec = nullptr;
-	size_t alloc = (size_t)((n + 15) / 16 * 16 + 16);
-	CUDA_TRY(cudaMalloc(&d_text, alloc));
-	cudaError_t e = cudaMemcpy(d_text, h_text, n, cudaMemcpyHostToDevice);
-	if (e == cudaSuccess) e = cudaMemset(d_text + n, 0, alloc - n);
-	if (e != cudaSuccess) { cudaFree(d_text); snprintf(g_err, sizeof g_err, "H2D copy failed: %s", cudaGetErrorString(e)); return AGB_ERR_CUDA; }
-	if ((want & AGB_WANT_RECORDS) && capacity) {
-		e = cudaMalloc(&d_rec, capacity * sizeof(agb_record));
-		if (e != cudaSuccess) { cudaFree(d_text); snprintf(g_err, sizeof g_err, "cudaMalloc(records) failed: %s", cudaGetErrorString(e)); return AGB_ERR_CUDA; }
+	if ((want & AGB_WANT_RECORDS) && capacity && !records) return AGB_ERR_ARG;
+	memset(res, 0, sizeof *res);
+	const agb_desc &d = p->d;
+	int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
+	if (dev < 0 || dev >= 64) return AGB_ERR_ARG;
+	std::lock_guard<std::mutex> lk(g_ws_mu);
+	Workspace &W = g_ws[dev];
+	int rc = ws_prepare(W, n); if (rc) return rc;
+	if (!W.s_copy) {
+		CUDA_TRY(cudaStreamCreateWithFlags(&W.s_copy, cudaStreamNonBlocking));
+		CUDA_TRY(cudaStreamCreateWithFlags(&W.s_comp, cudaStreamNonBlocking));
+		for (int i = 0; i < STAGE_BUFS; i++) CUDA_TRY(cudaEventCreateWithFlags(&W.ev_copy[i], cudaEventDisableTiming));
 	}
-	int rc = scan_device_impl(p->d, d_text, n, want, -1, d_rec, capacity, 0, res);
-	if (rc == AGB_OK && d_rec && res->n_records) {
-		e = cudaMemcpy(records, d_rec, res->n_records * sizeof(agb_record), cudaMemcpyDeviceToHost);
-		if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "D2H copy failed: %s", cudaGetErrorString(e)); rc = AGB_ERR_CUDA; }
+	const size_t need = (size_t)((n + 15) / 16 * 16 + 4096);
+	if (need > W.h2d_cap) {
+		if (W.h2d_text) cudaFree(W.h2d_text);
+		W.h2d_text = nullptr; W.h2d_cap = 0;
+		CUDA_TRY(cudaMalloc(&W.h2d_text, need)); W.h2d_cap = need;
 	}
-	cudaFree(d_text); if (d_rec) cudaFree(d_rec);
-	return rc;
+	if ((want & AGB_WANT_RECORDS) && capacity > W.h2d_rec_cap) {
+		if (W.h2d_rec) cudaFree(W.h2d_rec);
+		W.h2d_rec = nullptr; W.h2d_rec_cap = 0;
+		CUDA_TRY(cudaMalloc(&W.h2d_rec, capacity * sizeof(agb_record))); W.h2d_rec_cap = capacity;
+	}
+	rc = ws_upload_desc(W, d, W.s_comp); if (rc) return rc;
+	cudaPointerAttributes attr; memset(&attr, 0, sizeof attr);
+	bool pinned = n && cudaPointerGetAttributes(&attr, h_text) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+	cudaGetLastError();
+	if (!pinned && n && !W.stage[0]) for (int i = 0; i < STAGE_BUFS; i++) CUDA_TRY(cudaMallocHost(&W.stage[i], H2D_SLICE));
+	const bool use_front = front_usable(d) && n > 0;
+	const uint64_t words_per_slice = H2D_SLICE / 512, n_slices = (n + H2D_SLICE - 1) / H2D_SLICE;
+	CUDA_TRY(cudaMemsetAsync(W.totals, 0, 16 * sizeof(unsigned long long), W.s_comp));
+	CUDA_TRY(cudaEventRecord(W.e0, W.s_comp));
+	/* zero the slack after the text once (stage 1 reads whole 16-byte chunks, stage 2 whole groups) */
+	CUDA_TRY(cudaMemsetAsync(W.h2d_text + (n & ~(uint64_t)15), 0, need - (n & ~(uint64_t)15), W.s_copy));
+	for (uint64_t i = 0; i < n_slices; i++) {
+		const uint64_t off = i * H2D_SLICE, len = std::min<uint64_t>(H2D_SLICE, n - off);
+		const int sb = (int)(i % STAGE_BUFS);
+		if (pinned) {
+			CUDA_TRY(cudaMemcpyAsync(W.h2d_text + off, (const uint8_t *)h_text + off, len, cudaMemcpyHostToDevice, W.s_copy));
+		} else {
+			if (i >= STAGE_BUFS) CUDA_TRY(cudaEventSynchronize(W.ev_copy[sb]));     /* that staging buffer has been consumed */
+			par_memcpy(W.stage[sb], (const uint8_t *)h_text + off, len);
+			CUDA_TRY(cudaMemcpyAsync(W.h2d_text + off, W.stage[sb], len, cudaMemcpyHostToDevice, W.s_copy));
+		}
+		CUDA_TRY(cudaEventRecord(W.ev_copy[sb], W.s_copy));
+		/* stage 1 on the previous slice: its last chunk looks 4 bytes into this one, which is now on its way */
+		if (use_front) {
+			CUDA_TRY(cudaStreamWaitEvent(W.s_comp, W.ev_copy[sb], 0));
+			if (i > 0) { rc = front_launch(d, W, W.h2d_text, n, (i - 1) * words_per_slice, i * words_per_slice, true, W.s_comp); if (rc) return rc; }
+		}
+	}
+	if (n_slices) {
+		CUDA_TRY(cudaStreamWaitEvent(W.s_comp, W.ev_copy[(n_slices - 1) % STAGE_BUFS], 0));
+		if (use_front) { rc = front_launch(d, W, W.h2d_text, n, (n_slices - 1) * words_per_slice, ~0ull, true, W.s_comp); if (rc) return rc; }
+	}
+	CUDA_TRY(cudaEventRecord(W.e1, W.s_comp));
+	if (use_front) { rc = refine_launch(d, W, W.h2d_text, n, W.s_comp); if (rc) return rc; }
+	rc = records_launch(d, W, W.h2d_text, n, use_front, want, -1, W.h2d_rec, capacity, W.s_comp); if (rc) return rc;
+	CUDA_TRY(cudaEventRecord(W.e2, W.s_comp));
+	rc = fetch_result(W, want, capacity, W.s_comp, res); if (rc) return rc;
+	if (res->n_records) {
+		CUDA_TRY(cudaMemcpyAsync(records, W.h2d_rec, res->n_records * sizeof(agb_record), cudaMemcpyDeviceToHost, W.s_comp));
+		CUDA_TRY(cudaStreamSynchronize(W.s_comp));
+	}
+	CUDA_TRY(cudaStreamSynchronize(W.s_copy));
+	CUDA_TRY(cudaEventElapsedTime(&res->ms_front, W.e0, W.e1));
+	CUDA_TRY(cudaEventElapsedTime(&res->ms_records, W.e1, W.e2));
+	return AGB_OK;
 }
 
 extern "C" int agb_scan_fd(const agb_pattern *p, int fd, int want, agb_record *records, uint64_t capacity, agb_result *res)

@@ -1,0 +1,357 @@
+#!/usr/bin/env python3
+"""bench.py -- the driver's measurement contract for agrep-b200.
+
+One "step" = one pass of the scan path over the whole synthetic corpus:
+    agrep -2 'because each' <64 GiB newline-delimited text>      (BASELINE.json configs[1])
+i.e. stage 1 (k_front, the HBM-bound kernel) + stage 2 (k_records) + the ordered list of matching records;
+with N > 1 the 64 GiB are sharded by byte range over the ranks (records never cross a shard: the corpus
+is made of independent 4 KiB pages) and the match lists are gathered with NCCL.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one rank per GPU under torchrun)
+  python bench.py --impl reference ...                      the reference's own CPU scan on the host cores
+
+Prints ONE JSON line (rank 0).  `value` = corpus bytes / device time (inputs resident in HBM);
+`e2e` = the same scan through agb_scan_host() on pinned HOST buffers, H2D and result D2H inside the timing;
+`roofline` = k_front's algorithmic bytes / its CUDA-event duration against MEASURED_PEAKS.json;
+`cpu_baseline` = the unmodified reference binary (oracle/_ref/agrep, built from /root/reference) on a
+bounded sample of the same corpus on the box's host cores.
+"""
+import argparse, ctypes, json, os, shutil, statistics, subprocess, sys, tempfile, threading, time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PATTERN = "because each"          # 12-char literal made of two adjacent vocabulary words
+K = 2
+TOTAL_GIB = float(os.environ.get("AGB_BENCH_GIB", "64"))
+E2E_GIB = float(os.environ.get("AGB_BENCH_E2E_GIB", "4"))
+CPU_SAMPLE_MIB = int(os.environ.get("AGB_BENCH_CPU_MIB", "1024"))
+NEEDLE_EVERY = 4096               # one planted line per 16 MiB, with 0..3 substitutions
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "agrep")
+PAGE = 4096
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (of fallback)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's own CPU implementation of the path, all host threads: one unmodified `agrep -c -n -2`
+    process per core, each over its own record-aligned shard of the same synthetic corpus (the program is
+    single-threaded by construction).  -n forces the asearch() automaton."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import agrep_b200 as ag
+    cores = os.cpu_count() or 1
+    kind = "reference" if os.path.exists(REF_BIN) else "port"
+    shard = (256 << 20) // PAGE * PAGE      # large enough that process start-up is noise next to the scan
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > cores * shard * 1.2 else tempfile.gettempdir()
+    tmp = tempfile.mkdtemp(prefix="agb_ref_", dir=base)
+    try:
+        files = [os.path.join(tmp, "shard%03d.txt" % i) for i in range(cores)]
+
+        def gen(i):
+            data = ag.corpus_host(shard, first_page=i * (shard // PAGE), needle=PATTERN, needle_every=NEEDLE_EVERY, needle_maxedits=3)
+            with open(files[i], "wb") as f:
+                f.write(data)
+        th = [threading.Thread(target=gen, args=(i,)) for i in range(cores)]
+        [t.start() for t in th]; [t.join() for t in th]
+        total = shard * cores
+
+        def step():
+            if kind == "reference":
+                ps = [subprocess.Popen([REF_BIN, "-V0", "-c", "-n", "-%d" % K, PATTERN, f], stdout=subprocess.PIPE,
+                                       stderr=subprocess.DEVNULL) for f in files]
+                return sum(int((p.communicate()[0] or b"0").split()[0]) if p.wait() is not None else 0 for p in ps)
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import _oracle
+            a = _oracle.compile(PATTERN, k=K, linenum=1)
+            res = [0] * cores
+
+            def one(i):
+                res[i] = _oracle.scan(a, open(files[i], "rb").read(), want_records=False)[0]
+            th = [threading.Thread(target=one, args=(i,)) for i in range(cores)]
+            [t.start() for t in th]; [t.join() for t in th]
+            return sum(res)
+        for _ in range(args.warmup):
+            matched = step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            matched = step()
+        dt = (time.perf_counter() - t0) / max(1, args.steps)
+        val = total / dt / 1e9
+        sample = "%d shards x %d MiB of the same synthetic corpus, one `agrep -V0 -c -n -%d` process per host core" % (cores, shard >> 20, K)
+        print(json.dumps({
+            "impl": "reference", "metric": "text_scan_throughput", "value": val, "unit": "GB/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u32 bitwise", "data": "synthetic",
+            "config": workload_config(args.gpus), "matches_per_step": matched,
+            "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return 0
+
+
+def workload_config(n_gpus):
+    return {"workload": "agrep -%d '%s' over %.0f GiB synthetic newline-delimited ASCII (BASELINE.json configs[1]%s)"
+                        % (K, PATTERN, TOTAL_GIB, "" if n_gpus == 1 else ", sharded as configs[4]"),
+            "pattern": PATTERN, "k": K, "records": "newline", "corpus_gib": TOTAL_GIB,
+            "parallelism": "1 GPU" if n_gpus == 1 else "%d byte-range shards, NCCL all_gather of match lists" % n_gpus,
+            "l2": "input per GPU is far larger than the 126 MB L2; no flush needed",
+            "output": "count + ordered (begin,end) list of matching records"}
+
+
+# ----------------------------------------------------------------------------------------------------
+def cpu_baseline(ag, corpus_t, n_local):
+    """rank 0, N=1: the unmodified reference binary on a bounded sample of the SAME corpus (one core: the
+    program is single-threaded), `-n` forcing the asearch() automaton whose semantics we reproduce."""
+    import torch
+    nbytes = min(CPU_SAMPLE_MIB << 20, n_local) // PAGE * PAGE
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > nbytes * 1.5 else tempfile.gettempdir()
+    path = os.path.join(base, "agb_cpu_sample_%d.txt" % os.getpid())
+    try:
+        with open(path, "wb") as f:
+            step = 256 << 20
+            for off in range(0, nbytes, step):
+                f.write(corpus_t[off:min(off + step, nbytes)].cpu().numpy().tobytes())
+        best, count = None, None
+        if os.path.exists(REF_BIN):
+            kind = "reference"
+            for _ in range(2):
+                t0 = time.perf_counter()
+                out = subprocess.run([REF_BIN, "-V0", "-c", "-n", "-%d" % K, PATTERN, path], capture_output=True).stdout
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+                count = int(out.split()[0]) if out.split() else 0
+        else:
+            kind = "port"
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import _oracle
+            a = _oracle.compile(PATTERN, k=K, linenum=1)
+            data = open(path, "rb").read()
+            t0 = time.perf_counter()
+            count = _oracle.scan(a, data, want_records=False)[0]
+            best = time.perf_counter() - t0
+        return {"value": nbytes / best / 1e9, "unit": "GB/s", "cores": 1, "kind": kind,
+                "sample": "first %d MiB of the benchmark corpus, `agrep -V0 -c -n -%d '%s'`, page-cached, best of 2" % (nbytes >> 20, K, PATTERN),
+                "matched_in_sample": count, "host_cores_available": os.cpu_count()}, nbytes, count
+    finally:
+        try:
+            os.unlink(path)
+        except OSError:
+            pass
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import agrep_b200 as ag
+    from agrep_b200 import _lib
+    L = _lib.lib()                      # raises if the CUDA library is missing: there is no fallback
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    total = int(TOTAL_GIB * (1 << 30)) // (PAGE * world) * (PAGE * world)
+    n_local = total // world
+    first_page = rank * (n_local // PAGE)
+    corpus = torch.empty(n_local + 4096, dtype=torch.uint8, device=dev)
+    corpus[n_local:].zero_()
+    stream = torch.cuda.current_stream().cuda_stream
+    ag.corpus_device(corpus.data_ptr(), n_local, stream=stream, first_page=first_page, needle=PATTERN,
+                     needle_every=NEEDLE_EVERY, needle_maxedits=3)
+    torch.cuda.synchronize()
+
+    pat = ag.Pattern(PATTERN, k=K)
+    CAP = 1 << 22
+    recs = torch.zeros((CAP, 4), dtype=torch.int64, device=dev)       # agb_record = 4 x int64 (level+pad packed in the last)
+    cnt_t = torch.zeros(1, dtype=torch.int64, device=dev)
+    all_cnt = torch.zeros(world, dtype=torch.int64, device=dev)
+
+    def step():
+        res = pat.scan_device(corpus.data_ptr(), n_local, stream=stream, d_records=recs.data_ptr(), capacity=CAP)
+        gathered = res.n_records
+        if world > 1:
+            # shard-local offsets -> corpus offsets, then NCCL gather of the variable-length lists (padded to the max)
+            cnt_t[0] = res.n_records
+            dist.all_gather_into_tensor(all_cnt, cnt_t)
+            m = int(all_cnt.max().item())
+            if m:
+                blk = recs[:m].clone()
+                blk[:res.n_records, 0:2] += rank * n_local
+                out = torch.empty((world * m, 4), dtype=torch.int64, device=dev)
+                dist.all_gather_into_tensor(out, blk)
+            gathered = int(all_cnt.sum().item())
+        return res, gathered
+
+    for _ in range(args.warmup):
+        res, gathered = step()
+    launches0 = L.agb_kernel_launches()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    front_ms, rec_ms = [], []
+    e0.record()
+    for _ in range(args.steps):
+        res, gathered = step()
+        front_ms.append(res.ms_front); rec_ms.append(res.ms_records)
+    e1.record()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    launches = L.agb_kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    matched_total = gathered
+
+    # ---- end to end through the host-buffer entry point (pinned host memory, H2D + result D2H inside the timing)
+    n_e2e = min(int(E2E_GIB * (1 << 30)), n_local) // PAGE * PAGE
+    host = torch.empty(n_e2e, dtype=torch.uint8, pin_memory=True)
+    host.copy_(corpus[:n_e2e])
+    torch.cuda.synchronize()
+    hrec = (_lib.Record * 65536)()
+    hres = _lib.Result()
+
+    def e2e_step():
+        rc = L.agb_scan_host(pat._h, ctypes.c_void_p(host.data_ptr()), n_e2e, _lib.WANT_RECORDS, hrec, 65536, ctypes.byref(hres))
+        if rc != 0:
+            raise RuntimeError(L.agb_last_error().decode())
+        return hres.n_records
+    for _ in range(2):
+        e2e_step()
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    E2E_STEPS = 3
+    for _ in range(E2E_STEPS):
+        nrec = e2e_step()
+    dt = (time.perf_counter() - t0) / E2E_STEPS
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = n_e2e * world / float(t.item()) / 1e9
+
+    cpu = None
+    if rank == 0 and world == 1:
+        cpu, nsample, cpu_count = cpu_baseline(ag, corpus, n_local)
+        # the same sample through the CUDA path must agree with the reference binary, bit for bit
+        r = pat.scan_device(corpus.data_ptr(), nsample, stream=stream)
+        cpu["gpu_matched_in_sample"] = int(r.n_matched)
+        if cpu_count is not None and int(r.n_matched) != cpu_count:
+            raise SystemExit("PARITY FAILURE: reference counted %d records in the sample, CUDA path %d" % (cpu_count, r.n_matched))
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        fm = statistics.mean(front_ms)
+        achieved = n_local / (fm * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "k_front_traffic.json")))
+        except Exception:
+            pass
+        value = total / (ms_step * 1e-3) / 1e9
+        out = {
+            "metric": "text_scan_throughput", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32 bitwise", "data": "synthetic", "config": workload_config(world),
+            "matching_records": matched_total, "matching_records_per_s": matched_total / (ms_step * 1e-3),
+            "roofline": {"bound": "hbm", "kernel": "k_front (stage 1, anchor filter)", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": n_local, "ms_per_launch": fm,
+                         "stage2_ms_per_step": statistics.mean(rec_ms),
+                         "traffic": (traffic or {}).get("dram_bytes_per_launch") if traffic else None,
+                         "traffic_note": (traffic or {}).get("note") if traffic else "no ncu --set full capture yet"},
+            "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": n_e2e, "d2h_bytes_per_step": 128 + 32 * int(nrec),
+                    "what": "agb_scan_host() on a pinned host buffer holding the first %.1f GiB of each rank's shard; "
+                            "64 MiB H2D slices overlapped with stage 1; wall clock incl. result read-back" % (n_e2e / (1 << 30))},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if cpu:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out))
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

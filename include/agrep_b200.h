@@ -83,6 +83,11 @@ typedef struct agb_desc {
 	uint32_t anchor[AGB_MAXANCHOR];           /* little-endian packed anchor bytes           */
 	uint32_t anchor_fold;                     /* OR-mask applied to text and anchors (0x20 per letter byte under -i / bm) */
 	uint32_t anchor_mask;                     /* 0xFFFFFFFF, 0x00FFFFFF or 0x0000FFFF        */
+	/* local verification of anchor hits (stage 1.5): anchor i starts anchor_off[i] positions after the
+	 * separator slot; the pattern proper has pat_len positions; refine = 1 when a hit can be checked on the
+	 * window [p - off - k, p + pat_len - off + k) alone (single pattern, no '#', no -v/-p) */
+	int32_t  refine, pat_len;
+	int32_t  anchor_off[AGB_MAXANCHOR];
 } agb_desc;
 
 typedef struct agb_pattern agb_pattern;       /* opaque: agb_desc + bookkeeping              */

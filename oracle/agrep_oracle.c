@@ -297,8 +297,8 @@ static void rec_close(recstate *r, uint64_t i, int cond, int level)
 	if (cond && rec_counts(r, i)) {
 		if (r->recs && (uint64_t)r->matched < r->cap) {
 			orc_record *q = &r->recs[r->matched];
-			q->begin = r->lasti - 1;                 /* buffer index -> file offset */
-			q->end = i - (uint64_t)L - 1;            /* print_end + 1 (exclusive), as a file offset */
+			q->begin = (int64_t)r->lasti - 1;        /* buffer index -> file offset (-1: the virtual '\n') */
+			q->end = (int64_t)(i - (uint64_t)L - 1); /* print_end + 1 (exclusive), as a file offset */
 			q->ordinal = r->j; q->level = level;
 		}
 		r->matched++;
@@ -425,8 +425,8 @@ static int64_t scan_bm(const orc_automaton *a, const unsigned char *text, uint64
 		}
 		if (hit) {
 			if (recs && matched < cap) {
-				/* same record convention as the automaton path: begin at the previous line's '\n' */
-				recs[matched].begin = ls ? ls - 1 : 0; recs[matched].end = le; recs[matched].ordinal = (int64_t)line; recs[matched].level = 0;
+				/* same record convention as the automaton path: begin at the previous line's '\n' (-1 = the virtual one) */
+				recs[matched].begin = (int64_t)ls - 1; recs[matched].end = (int64_t)le; recs[matched].ordinal = (int64_t)line; recs[matched].level = 0;
 			}
 			matched++;
 		}

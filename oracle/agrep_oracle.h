@@ -65,8 +65,8 @@ typedef struct {
 } orc_automaton;
 
 typedef struct {
-	uint64_t begin;   /* file offset of lasti   (first byte of the delimiter that closed the previous record, or 0) */
-	uint64_t end;     /* file offset one past print_end (= first byte of this record's closing delimiter)          */
+	int64_t  begin;   /* file offset of lasti   (first byte of the delimiter that closed the previous record; -1 = virtual '\n') */
+	int64_t  end;     /* file offset one past print_end (= first byte of this record's closing delimiter)          */
 	int64_t  ordinal; /* j at the call of output() (agrep.c:3805); -n prints j-1 (+1 when DELIMITER)                */
 	int      level;   /* best-match mode only: smallest error level that matched, else -1                           */
 } orc_record;

@@ -1,0 +1,72 @@
+"""The drop-in proof: the reference program linked against libagrepb200_dropin.so (oracle/_ref/agrep_dropin:
+the reference's own main(), option parser, exec() and output(); only bitap/asearch/asearch0/asearch1/sgrep/
+fill_buf come from this repo and run on the GPU) must print byte-for-byte what the unmodified reference
+(oracle/_ref/agrep) prints.  Both binaries are built here by oracle/Makefile and travel to the GPU box."""
+import os, subprocess, tempfile
+import pytest
+import _corpus
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "agrep")
+DROP = os.path.join(ROOT, "oracle", "_ref", "agrep_dropin")
+
+
+@pytest.fixture(scope="module")
+def files():
+    if not (os.path.exists(REF) and os.path.exists(DROP)):
+        pytest.skip("oracle/_ref binaries not built")
+    d = tempfile.mkdtemp(prefix="agb_dropin_")
+    paths = {}
+    for name, data in (("a.txt", _corpus.make_text(3000, seed=11)), ("b.txt", _corpus.make_text(2000, seed=12, trailing_newline=False)),
+                       ("para.txt", _corpus.make_text(2500, seed=13, paragraphs=True))):
+        paths[name] = os.path.join(d, name)
+        open(paths[name], "wb").write(data)
+    yield paths
+    for p in paths.values():
+        os.unlink(p)
+    os.rmdir(d)
+
+
+def run(binary, args):
+    p = subprocess.run([binary] + args, capture_output=True, timeout=120, stdin=subprocess.DEVNULL)
+    return p.returncode, p.stdout, p.stderr
+
+
+CASES = [
+    (["-c", "the"], ["a.txt"]),                                  # sgrep -> bm, count
+    (["the"], ["a.txt"]),                                        # sgrep -> bm, records printed
+    (["-c", "the"], ["a.txt", "b.txt"]),                         # two files: "file: N" lines
+    (["-h", "government"], ["a.txt", "b.txt"]),
+    (["-l", "government"], ["a.txt", "b.txt"]),
+    (["-w", "-c", "the"], ["b.txt"]),
+    (["-n", "because each"], ["a.txt"]),                         # bitap exact, line numbers
+    (["-n", "-1", "because each"], ["a.txt"]),                   # asearch
+    (["-n", "-2", "-i", "Government"], ["a.txt", "b.txt"]),
+    (["-c", "-n", "-3", "government"], ["a.txt"]),
+    (["-n", "-5", "governmental"], ["a.txt"]),                   # asearch0
+    (["-n", "-2", "-S2", "between both"], ["a.txt"]),            # asearch1
+    (["-n", "-v", "-1", "the"], ["b.txt"]),                      # inverse
+    (["-c", "-n", "-v", "the"], ["a.txt"]),
+    (["-n", "-w", "-1", "matching"], ["a.txt"]),
+    (["-n", "st.t[a-e]"], ["a.txt"]),
+    (["-n", "-b", "-1", "homogeneous"], ["a.txt"]),
+    (["-n", "-d", "$$", "-1", "because each"], ["para.txt"]),    # paragraph records
+    (["-c", "-n", "-d", "$$", "-w", "world"], ["para.txt"]),
+    (["-n", "-y", "-B", "goverment of the peple"], ["a.txt"]),   # best-match sweep, no prompt
+    (["-n", "-L2", "-1", "the"], ["a.txt"]),                     # output limit
+    (["-s", "the"], ["a.txt"]),
+    (["-n", "^the"], ["a.txt"]),
+    (["-n", "world$"], ["b.txt"]),
+    (["-n", "a#d;world"], ["a.txt"]),
+]
+
+
+@pytest.mark.parametrize("args,names", CASES)
+def test_same_stdout_as_reference(files, args, names):
+    fl = [files[n] for n in names]
+    r = run(REF, ["-V0"] + args + fl)
+    d = run(DROP, ["-V0"] + args + fl)
+    assert d[2].replace(b"agrep_dropin", b"agrep") == r[2], (d[2], r[2])
+    assert d[1] == r[1]
+    assert d[0] == r[0]

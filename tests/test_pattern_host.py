@@ -103,14 +103,14 @@ def test_anchor_plan():
     d = ag.Pattern("because each", k=3).desc           # 4 runs of 3
     assert d.n_anchors == 4 and d.anchor_len == 3 and d.anchor_mask == 0xFFFFFF
     d = ag.Pattern("the").desc                          # bm: always case folded
-    assert d.n_anchors == 1 and d.anchor_len == 3 and d.anchor_fold == 0x202020
+    assert d.n_anchors == 1 and d.anchor_len == 3 and d.anchor_fold == 0x20202020 and d.anchor[0] == 0x656874
     assert ag.Pattern("because each", k=2, inverse=1).desc.plan == ag.api.PLAN_ALL
     assert ag.Pattern("government", k=2, ins_free=1).desc.plan == ag.api.PLAN_ALL
     assert ag.Pattern("a.b.c.d", k=1, linenum=1).desc.plan == ag.api.PLAN_ALL
     d = ag.Pattern("state,world", linenum=1).desc       # OR: one anchor per alternative
     assert d.n_anchors == 2
     d = ag.Pattern("Hello World", k=1, nocase=1).desc
-    assert d.anchor_fold != 0 and all((d.anchor[i] & d.anchor_fold) == d.anchor_fold for i in range(d.n_anchors))
+    assert d.anchor_fold == 0x20202020 and all((d.anchor[i] & d.anchor_fold) == d.anchor_fold for i in range(d.n_anchors))
 
 
 def test_corpus_generator_properties():
