@@ -28,6 +28,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <unistd.h>
+#include <sys/stat.h>
 #include <mutex>
 #include <atomic>
 #include <algorithm>
@@ -55,8 +56,8 @@ extern "C" int agb_set_device(int dev) { CUDA_TRY(cudaSetDevice(dev)); return AG
 #define FRONT_STAGE_CHUNKS (FRONT_THREADS * FRONT_CH)     /* 1024 chunks = 16 KiB = 32 bitmap words per stage */
 #define FRONT_STAGE_BYTES  (FRONT_STAGE_CHUNKS * 16)
 #define FRONT_SLOT_BYTES   (FRONT_STAGE_BYTES + 16)       /* + the 16 bytes that follow: the last chunk's windows look 3 bytes ahead */
-#define FRONT_NST     4                                   /* stages in flight per CTA (64 KiB), 3 CTAs per SM  */
-#define FRONT_CTAS_PER_SM 3
+#define FRONT_NST     2                                   /* stages in flight per CTA (32 KiB); 6 CTAs = 48 warps per SM: measured best */
+#define FRONT_CTAS_PER_SM 6
 #define FRONT_WORDS_PER_STAGE (FRONT_STAGE_CHUNKS / 32)
 
 struct FrontParams {
@@ -152,16 +153,25 @@ k_front(const FrontParams P)
 		bulk_g2s(s_ring + slot * FRONT_SLOT_BYTES, P.text + off, bytes, &s_bar[slot]);
 	};
 	if (tid == 0) for (int i = 0; i < FRONT_NST; i++) issue(i);
-	for (uint64_t it = 0;; it++) {
-		const uint64_t sg = P.stage_begin + blockIdx.x + it * gridDim.x;
+	const uint32_t warp_in_cta = tid >> 5;
+	for (uint32_t it = 0;; it++) {
+		const uint64_t sg = P.stage_begin + blockIdx.x + (uint64_t)it * gridDim.x;
 		if (sg >= P.stage_end) break;
-		const uint32_t slot = (uint32_t)(it % FRONT_NST);
-		mbar_wait(&s_bar[slot], (uint32_t)((it / FRONT_NST) & 1));
+		const uint32_t slot = it % FRONT_NST;
+		mbar_wait(&s_bar[slot], (it / FRONT_NST) & 1u);
 		const uint8_t *st = s_ring + slot * FRONT_SLOT_BYTES;
+		/* per-stage scalars, so that the per-chunk bookkeeping below is 32-bit */
+		const uint64_t left = P.n_chunks - sg * FRONT_STAGE_CHUNKS;                    /* chunks from the start of this stage to EOF */
+		const uint32_t rem = left > 0xFFFF0000ull ? 0xFFFF0000u : (uint32_t)left;
+		uint32_t *bm = P.bitmap + sg * FRONT_WORDS_PER_STAGE + warp_in_cta;
+		/* full = every chunk of the stage exists and none is among the last two of the text: no per-chunk EOF logic */
+		const bool full = left >= FRONT_STAGE_CHUNKS + 2;
 #pragma unroll
 		for (int c = 0; c < FRONT_CH; c++) {
 			const uint32_t idx = c * FRONT_THREADS + tid;
 			uint4 v = *reinterpret_cast<const uint4 *>(st + idx * 16);
+			/* the first word of the next chunk (a 4-way bank conflict, measured cheaper than SHFL + a predicated LDS:
+			 * 4905 vs 4787 GB/s, profiles/round1_front_variants.md) */
 			uint32_t x4 = *reinterpret_cast<const uint32_t *>(st + idx * 16 + 16);
 			if (FOLD) { v.x |= P.fold; v.y |= P.fold; v.z |= P.fold; v.w |= P.fold; x4 |= P.fold; }
 			uint32_t acc = 0xffffffffu;
@@ -169,41 +179,51 @@ k_front(const FrontParams P)
 			acc = windows_test<NA, MASKED, POLY>(v.y, v.z, P, acc);
 			acc = windows_test<NA, MASKED, POLY>(v.z, v.w, P, acc);
 			acc = windows_test<NA, MASKED, POLY>(v.w, x4, P, acc);
-			const uint64_t chunk = sg * FRONT_STAGE_CHUNKS + idx;
-			/* the last chunks are always passed on: a match may run into the delimiter appended at EOF (bitap.c:161-165),
-			 * and their look-ahead bytes may not exist */
-			const bool flag = (chunk < P.n_chunks) && (acc == 0 || chunk + 2 >= P.n_chunks);
-			const uint32_t word = __ballot_sync(0xffffffffu, flag);
-			if (lane == 0 && chunk < P.n_chunks) P.bitmap[chunk >> 5] = word;
+			if (full) {
+				const uint32_t word = __ballot_sync(0xffffffffu, acc == 0);
+				if (lane == 0) bm[c * (FRONT_THREADS / 32)] = word;
+			} else {
+				/* the last chunks are always passed on: a match may run into the delimiter appended at EOF
+				 * (bitap.c:161-165), and their look-ahead bytes may not exist */
+				const bool flag = (idx < rem) && (acc == 0 || idx + 2 >= rem);
+				const uint32_t word = __ballot_sync(0xffffffffu, flag);
+				if (lane == 0 && idx < rem) bm[c * (FRONT_THREADS / 32)] = word;
+			}
 		}
 		__syncthreads();                       /* everyone is done reading this slot */
-		if (tid == 0) issue(it + FRONT_NST);   /* refill it with the stage FRONT_NST iterations ahead */
+		if (tid == 0) issue((uint64_t)it + FRONT_NST);   /* refill it with the stage FRONT_NST iterations ahead */
 	}
 }
 
 /* ================================================================================================
- * stage 2: records
+ * shared device pieces of stages 1.5 and 2: the recurrence, the match test, the text reader
  * ============================================================================================== */
-#define REC_THREADS 128          /* one thread per bitmap word: a block covers 128*512 B = 64 KiB of text */
-
-struct RecParams {
-	const uint8_t  *text;
-	const uint32_t *bitmap;      /* NULL: every chunk flagged */
-	uint64_t n, n_chunks, n_words;
-	const agb_desc *desc;        /* device copy */
-	uint32_t *tile_counts;       /* per block */
-	const uint64_t *tile_offsets;/* exclusive scan of tile_counts (emit pass) */
-	agb_record *records; uint64_t capacity;
-	unsigned long long *totals;  /* [0] matched, [1] flagged chunks, [2..10] level histogram, [11] emitted */
-	int emit;                    /* 0: count pass, 1: emit pass */
-	int levels;                  /* 1: best-match bookkeeping (smallest matching row) */
-	int want_level;              /* levels: report records whose smallest level <= want_level (-1: all matching) */
-};
-
 template <typename T> struct DevConsts {
 	T init1, noerr, endpos, dendpos;
 	int L, k, and_mode, inverse, kind, ci, cs, cd;
 };
+
+template <typename T, int NR> struct RecShared {
+	T mask[257];                 /* mask[256] = 0: "a byte outside the text" */
+	T reset[NR], start[NR];
+	uint8_t delim[2 * AGB_MAXDELIM + 2];
+	unsigned long long hist[AGB_MAXERR + 1];
+	int start_closes;
+};
+
+template <typename T, int NR>
+__device__ __forceinline__ void shared_init(RecShared<T, NR> &S, DevConsts<T> &C, const agb_desc *D, int nthreads)
+{
+	for (int i = threadIdx.x; i < 256; i += nthreads) S.mask[i] = (T)D->mask[i];
+	if (threadIdx.x == 0) { S.mask[256] = 0; S.start_closes = D->start_closes; }
+	if (threadIdx.x < NR) { S.reset[threadIdx.x] = (T)D->reset[threadIdx.x]; S.start[threadIdx.x] = (T)D->start[threadIdx.x]; }
+	if (threadIdx.x < 2 * AGB_MAXDELIM + 2) S.delim[threadIdx.x] = D->delim[threadIdx.x];
+	if (threadIdx.x <= AGB_MAXERR) S.hist[threadIdx.x] = 0;
+	C.init1 = (T)D->init1; C.noerr = (T)D->noerr; C.endpos = (T)D->endpos; C.dendpos = (T)D->dendpos;
+	C.L = D->L; C.k = D->k; C.and_mode = D->and_mode; C.inverse = D->inverse; C.kind = D->delim_kind;
+	C.ci = D->cost_i; C.cs = D->cost_s; C.cd = D->cost_d;
+	__syncthreads();
+}
 
 /* text reader with a one-group (16 byte) register cache; positions are file offsets.
  * -1 is the virtual '\n' (bitap.c:140), n..n+L-1 the delimiter appended at EOF (bitap.c:161-165). */
@@ -240,6 +260,7 @@ __device__ __forceinline__ bool delim_ends_at(Reader &R, int64_t q, const uint8_
 	return (len % L) == 0;
 }
 
+/* one text byte through all rows: asearch.c:96-115 (unit costs), asearch1.c:88-97 (COSTS), bitap.c:175-176 (NR = 1) */
 template <typename T, int NR, bool COSTS>
 __device__ __forceinline__ void rows_step(T (&S)[NR], T cm, const DevConsts<T> &C)
 {
@@ -274,143 +295,6 @@ __device__ __forceinline__ bool match_cond(T r, const DevConsts<T> &C)
 	return ((r & C.endpos) != 0) != (C.inverse != 0);
 }
 
-template <typename T, int NR, bool COSTS>
-__global__ void __launch_bounds__(REC_THREADS)
-k_records(const RecParams P)
-{
-	__shared__ T s_mask[256];
-	__shared__ T s_reset[NR], s_start[NR];
-	__shared__ uint8_t s_delim[2 * AGB_MAXDELIM + 2];
-	__shared__ uint32_t s_scan[REC_THREADS];
-	__shared__ unsigned long long s_hist[AGB_MAXERR + 1];
-	const agb_desc *D = P.desc;
-	for (int i = threadIdx.x; i < 256; i += REC_THREADS) s_mask[i] = (T)D->mask[i];
-	if (threadIdx.x < NR) { s_reset[threadIdx.x] = (T)D->reset[threadIdx.x]; s_start[threadIdx.x] = (T)D->start[threadIdx.x]; }
-	if (threadIdx.x < 2 * AGB_MAXDELIM + 2) s_delim[threadIdx.x] = D->delim[threadIdx.x];
-	if (threadIdx.x <= AGB_MAXERR) s_hist[threadIdx.x] = 0;
-	DevConsts<T> C;
-	C.init1 = (T)D->init1; C.noerr = (T)D->noerr; C.endpos = (T)D->endpos; C.dendpos = (T)D->dendpos;
-	C.L = D->L; C.k = D->k; C.and_mode = D->and_mode; C.inverse = D->inverse; C.kind = D->delim_kind;
-	C.ci = D->cost_i; C.cs = D->cost_s; C.cd = D->cost_d;
-	__syncthreads();
-
-	const uint64_t gw = (uint64_t)blockIdx.x * REC_THREADS + threadIdx.x;     /* bitmap word of this thread */
-	const int L = C.L;
-	const int64_t n = (int64_t)P.n;
-	uint32_t word = 0;
-	if (gw < P.n_words) {
-		word = P.bitmap ? P.bitmap[gw] : 0xffffffffu;
-		uint64_t rem = P.n_chunks - gw * 32;
-		if (rem < 32) word &= (1u << rem) - 1u;
-	}
-	Reader R; R.init(P.text, P.n, s_delim, L);
-
-	uint32_t my_count = 0;
-	uint64_t out_pos = 0;
-	/* pass 0 counts; in emit mode pass 1 repeats the walk and writes at the scanned offsets */
-	for (int pass = 0; pass < (P.emit ? 2 : 1); pass++) {
-		uint32_t bits = word;
-		int64_t done_until = INT64_MIN;    /* everything before this offset belongs to records this thread already closed */
-		uint32_t cnt = 0;
-		while (bits) {
-			int b = __ffs(bits) - 1; bits &= bits - 1;
-			const int64_t c = (int64_t)(gw * 32 + b), lo = c * 16, hi = lo + 15;
-			int64_t s = -2;                /* record start to run from; -2: none */
-			if (done_until > lo) {
-				/* the record this thread closed last reaches into this chunk; what starts here starts at done_until */
-				if (done_until - 1 <= hi) s = done_until; else continue;
-			} else {
-				/* (a) the record that contains byte lo: ours iff its re-fed byte s-1 lies after the previous flagged chunk */
-				bool found = false;
-				if (c == 0) { s = 0; found = true; }
-				for (int64_t cc = c - 1; !found; cc--) {
-					if (cc < 0) { s = 0; found = true; break; }
-					uint32_t pw = P.bitmap ? P.bitmap[cc >> 5] : 0xffffffffu;
-					if (pw >> (cc & 31) & 1u) break;                  /* an earlier flagged chunk meets that record: not ours */
-					for (int64_t q = cc * 16 + 15; q >= cc * 16; q--)
-						if (delim_ends_at(R, q, s_delim, L, C.kind)) { s = q + 1; found = true; break; }
-				}
-				if (!found) {
-					/* (b) the first record whose re-fed byte lies inside this chunk */
-					for (int64_t q = lo; q <= hi && q < n; q++)
-						if (delim_ends_at(R, q, s_delim, L, C.kind)) { s = q + 1; break; }
-				}
-			}
-			/* run records while their re-fed byte (s-1) is at or before the end of this chunk */
-			while (s >= 0 && s - 1 <= hi && s <= n) {
-				T S[NR];
-				int64_t begin;
-				if (s == 0) {
-#pragma unroll
-					for (int r = 0; r < NR; r++) S[r] = s_start[r];
-					begin = D->start_closes ? -(int64_t)L : 0;
-				} else {
-#pragma unroll
-					for (int r = 0; r < NR; r++) S[r] = s_reset[r];
-					begin = s - L;
-				}
-				int64_t p = s, close_at = -1;
-				const int64_t limit = n + L;
-				for (; p < limit; p++) {
-					T cm = s_mask[R.get(p)];
-					rows_step<T, NR, COSTS>(S, cm, C);
-					if (S[0] & C.dendpos) { close_at = p; break; }
-				}
-				if (close_at < 0) { s = -2; done_until = limit + 1; break; }   /* never closed: dropped, as the reference does */
-				const int64_t end = close_at + 1 - L;
-				bool counts = (begin + 1 < n) && (begin + 1 <= end);           /* bitap.c:213 + agrep.c:3811 */
-				int level = C.k;
-				bool cond;
-				if (P.levels) {
-					level = -1;
-#pragma unroll
-					for (int r = 0; r < NR; r++) if (level < 0 && match_cond<T>(S[r], C)) level = r;
-					cond = level >= 0;
-					if (cond && counts && pass == 0) atomicAdd(&s_hist[level], 1ull);
-					if (cond && P.want_level >= 0 && level > P.want_level) cond = false;
-				} else cond = match_cond<T>(S[NR - 1], C);
-				if (cond && counts) {
-					if (pass == 1) {
-						uint64_t at = out_pos + cnt;
-						if (at < P.capacity) {
-							agb_record rec; rec.begin = begin; rec.end = end; rec.ordinal = 0; rec.level = level; rec.pad = 0;
-							P.records[at] = rec;
-						}
-					}
-					cnt++;
-				}
-				s = close_at + 1;
-				done_until = s;
-			}
-		}
-		if (pass == 0) {
-			my_count = cnt;
-			/* block scan of the per-thread counts */
-			s_scan[threadIdx.x] = cnt;
-			__syncthreads();
-			for (int off = 1; off < REC_THREADS; off <<= 1) {
-				uint32_t v = (threadIdx.x >= (unsigned)off) ? s_scan[threadIdx.x - off] : 0;
-				__syncthreads();
-				s_scan[threadIdx.x] += v;
-				__syncthreads();
-			}
-			if (!P.emit) {
-				if (threadIdx.x == REC_THREADS - 1) {
-					P.tile_counts[blockIdx.x] = s_scan[REC_THREADS - 1];
-					if (s_scan[REC_THREADS - 1]) atomicAdd(&P.totals[0], (unsigned long long)s_scan[REC_THREADS - 1]);
-				}
-				uint32_t fl = __popc(word);
-				fl = __reduce_add_sync(0xffffffffu, fl);
-				if ((threadIdx.x & 31) == 0 && fl) atomicAdd(&P.totals[1], (unsigned long long)fl);
-				__syncthreads();
-				if (P.levels && threadIdx.x <= AGB_MAXERR && s_hist[threadIdx.x]) atomicAdd(&P.totals[2 + threadIdx.x], s_hist[threadIdx.x]);
-			} else {
-				out_pos = P.tile_offsets[blockIdx.x] + (s_scan[threadIdx.x] - my_count);
-			}
-		}
-	}
-}
-
 /* ================================================================================================
  * stage 1.5: local verification of anchor hits
  *
@@ -419,14 +303,18 @@ k_records(const RecParams P)
  * text offset t aligns the pat_len pattern positions to text inside [t - off - k, t + pat_len - off + k), so
  * running the SAME recurrence over just that window (all rows started at Init[0], whose separator bit is the
  * always-on start state; no record logic, which can only remove bits) decides whether the hit can matter.
- * Chunks none of whose hits survive lose their bitmap bit.  Warps compact their 1024 chunks into a queue first,
- * so all 32 lanes verify candidates.
+ * Chunks none of whose hits survive lose their bitmap bit.  A warp first compacts the flagged chunks of its
+ * 32 bitmap words into a queue, so all lanes verify; each lane stages the few 16-byte groups around its chunk
+ * in shared memory and the lanes walk their windows in lockstep (same length for everyone).
  * ============================================================================================== */
 #define REFINE_THREADS 128
+#define REFINE_MAXG 8
 struct RefineParams {
 	const uint8_t *text; uint32_t *bitmap; uint64_t n, n_chunks, n_words;
 	const agb_desc *desc;
 	uint32_t fold, amask; int na;
+	int gb, ng;                  /* groups staged before the chunk, groups staged in total (<= REFINE_MAXG) */
+	int lo_off, hi_off;          /* the windows of a chunk at byte `base` lie inside [base - lo_off, base + hi_off) */
 	uint32_t anchor[AGB_MAXANCHOR]; int32_t off[AGB_MAXANCHOR];
 };
 
@@ -434,25 +322,20 @@ template <typename T, int NR, bool COSTS>
 __global__ void __launch_bounds__(REFINE_THREADS)
 k_refine(const RefineParams P)
 {
-	__shared__ T s_mask[257];
-	__shared__ uint8_t s_delim[2 * AGB_MAXDELIM + 2];
+	__shared__ RecShared<T, NR> SH;
 	__shared__ uint16_t s_queue[REFINE_THREADS / 32][1024];
 	__shared__ uint32_t s_keep[REFINE_THREADS / 32][32];
-	const agb_desc *D = P.desc;
-	for (int i = threadIdx.x; i < 256; i += REFINE_THREADS) s_mask[i] = (T)D->mask[i];
-	if (threadIdx.x == 0) s_mask[256] = 0;                   /* byte "256": outside the text, matches nothing */
-	if (threadIdx.x < 2 * AGB_MAXDELIM + 2) s_delim[threadIdx.x] = D->delim[threadIdx.x];
+	__shared__ __align__(16) uint32_t s_stage[REFINE_THREADS * (REFINE_MAXG * 4 + 1)];
 	DevConsts<T> C;
-	C.init1 = (T)D->init1; C.noerr = (T)D->noerr; C.endpos = (T)D->endpos; C.dendpos = (T)D->dendpos;
-	C.L = D->L; C.k = D->k; C.and_mode = D->and_mode; C.inverse = D->inverse; C.kind = D->delim_kind;
-	C.ci = D->cost_i; C.cs = D->cost_s; C.cd = D->cost_d;
-	const T init0 = (T)D->init0;
-	const int pat_len = D->pat_len, k = D->k;
-	__syncthreads();
+	shared_init<T, NR>(SH, C, P.desc, REFINE_THREADS);
+	const T init0 = (T)P.desc->init0;
+	const int pat_len = P.desc->pat_len, k = C.k, wlen = pat_len + 2 * k;
 	const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const int stride_w = P.ng * 4 + 1;                      /* odd number of words: lanes hit different banks */
+	uint32_t *my_stage = s_stage + threadIdx.x * stride_w;
+	const uint8_t *my_bytes = reinterpret_cast<const uint8_t *>(my_stage);
 	const uint64_t warp = ((uint64_t)blockIdx.x * REFINE_THREADS + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * REFINE_THREADS) >> 5;
 	const uint64_t n_groups = (P.n_words + 31) / 32;
-	Reader R; R.init(P.text, P.n, s_delim, C.L);
 	for (uint64_t g = warp; g < n_groups; g += nwarps) {
 		const uint64_t w = g * 32 + lane;
 		const uint32_t word = (w < P.n_words) ? P.bitmap[w] : 0u;
@@ -466,33 +349,62 @@ k_refine(const RefineParams P)
 		for (uint32_t b = word; b; b &= b - 1) s_queue[wib][pre++] = (uint16_t)(lane * 32 + (__ffs(b) - 1));
 		s_keep[wib][lane] = 0;
 		__syncwarp();
-		for (uint32_t qi = lane; qi < total; qi += 32) {
-			const uint32_t cidx = s_queue[wib][qi];
+		for (uint32_t q0 = 0; q0 < total; q0 += 32) {
+			const uint32_t qi = q0 + lane;
+			const bool active = qi < total;
+			const uint32_t cidx = active ? s_queue[wib][qi] : 0;
 			const int64_t chunk = (int64_t)(g * 1024 + cidx), base = chunk * 16;
-			bool keep = (uint64_t)chunk + 2 >= P.n_chunks;      /* the EOF chunks stay (appended delimiter, bitap.c:161-165) */
-			if (!keep) {
-				/* which windows of this chunk hit which anchor?  (exactly stage 1's test, exact compare) */
-				const uint4 v = __ldg(reinterpret_cast<const uint4 *>(P.text) + chunk);
-				const uint32_t nx = __ldg(reinterpret_cast<const uint32_t *>(P.text) + (chunk + 1) * 4);
-				uint32_t x[5] = { v.x | P.fold, v.y | P.fold, v.z | P.fold, v.w | P.fold, nx | P.fold };
-				for (int s = 0; s < 16 && !keep; s++) {
-					const uint32_t wv = __funnelshift_r(x[s >> 2], x[(s >> 2) + 1], (s & 3) * 8) & P.amask;
-					for (int a = 0; a < P.na && !keep; a++) {
-						if (wv != P.anchor[a]) continue;
-						const int64_t t = base + s, ws = t - P.off[a] - k, we = t + pat_len - P.off[a] + k;
-						T S[NR];
+			/* windows that touch the virtual '\n', the appended delimiter or the end of the buffer are not judged here */
+			bool keep = active && (base - P.lo_off < 0 || (uint64_t)(base + P.hi_off + 16) > P.n || (uint64_t)chunk + 2 >= P.n_chunks);
+			/* distinct window starts of this chunk: bit (32 + s - off_a) for a hit of anchor a at window s.  Two anchors
+			 * of one occurrence of the pattern ("beca" and "use " inside "because ") give the same start: judged once. */
+			uint64_t starts = 0;
+			if (active && !keep) {
+				const uint4 *src = reinterpret_cast<const uint4 *>(P.text) + (chunk - P.gb);
+				for (int gi = 0; gi < P.ng; gi++) {
+					const uint4 v = __ldg(src + gi);
+					my_stage[gi * 4 + 0] = v.x; my_stage[gi * 4 + 1] = v.y; my_stage[gi * 4 + 2] = v.z; my_stage[gi * 4 + 3] = v.w;
+				}
+				/* which of the 16 windows of the chunk equals which anchor (exactly stage 1's question) */
+				const uint32_t *cw = my_stage + P.gb * 4;
+				const uint32_t x0 = cw[0] | P.fold, x1 = cw[1] | P.fold, x2 = cw[2] | P.fold, x3 = cw[3] | P.fold, x4 = cw[4] | P.fold;
+				uint32_t wv[16];
+				wv[0] = x0; wv[1] = __funnelshift_r(x0, x1, 8); wv[2] = __funnelshift_r(x0, x1, 16); wv[3] = __funnelshift_r(x0, x1, 24);
+				wv[4] = x1; wv[5] = __funnelshift_r(x1, x2, 8); wv[6] = __funnelshift_r(x1, x2, 16); wv[7] = __funnelshift_r(x1, x2, 24);
+				wv[8] = x2; wv[9] = __funnelshift_r(x2, x3, 8); wv[10] = __funnelshift_r(x2, x3, 16); wv[11] = __funnelshift_r(x2, x3, 24);
+				wv[12] = x3; wv[13] = __funnelshift_r(x3, x4, 8); wv[14] = __funnelshift_r(x3, x4, 16); wv[15] = __funnelshift_r(x3, x4, 24);
 #pragma unroll
-						for (int r = 0; r < NR; r++) S[r] = init0;
-						T seen = 0;
-						for (int64_t q = ws; q < we; q++) {
-							rows_step<T, NR, COSTS>(S, s_mask[R.get(q)], C);
-							seen |= S[NR - 1];
-						}
-						keep = (seen & C.endpos) != 0;
-					}
+				for (int s = 0; s < 16; s++) wv[s] &= P.amask;
+				for (int a = 0; a < P.na; a++) {
+					const uint32_t A = P.anchor[a];
+					uint32_t m = 0;
+#pragma unroll
+					for (int s = 0; s < 16; s++) m |= (wv[s] == A ? 1u : 0u) << s;
+					starts |= (uint64_t)m << (32 - P.off[a]);          /* off <= 31 is guaranteed by refine_geometry() */
 				}
 			}
+			/* walk the windows: round r takes every lane's r-th distinct start, so the lanes stay together */
+			while (__ballot_sync(0xffffffffu, starts != 0 && !keep)) {
+				const bool run = starts != 0 && !keep;
+				int64_t ws = 0;
+				if (run) {
+					const int bit = __ffsll((long long)starts) - 1;
+					starts &= starts - 1;
+					ws = (int64_t)P.gb * 16 + (bit - 32) - k;          /* offset inside this lane's staged bytes */
+				}
+				T S[NR];
+#pragma unroll
+				for (int r = 0; r < NR; r++) S[r] = init0;
+				T seen = 0;
+				for (int q = 0; q < wlen; q++) {
+					const int c = run ? my_bytes[ws + q] : 0;
+					rows_step<T, NR, COSTS>(S, SH.mask[c], C);
+					seen |= S[NR - 1];
+				}
+				if (run && (seen & C.endpos) != 0) keep = true;
+			}
 			if (keep) atomicOr(&s_keep[wib][cidx >> 5], 1u << (cidx & 31));
+			__syncwarp();
 		}
 		__syncwarp();
 		const uint32_t nw = s_keep[wib][lane];
@@ -501,23 +413,262 @@ k_refine(const RefineParams P)
 	}
 }
 
-/* exclusive scan of the per-tile counts (one block; the array has n/64KiB entries) */
-__global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *counts, uint64_t *offsets, uint64_t n_tiles)
+/* ================================================================================================
+ * stage 2: records
+ * ============================================================================================== */
+#define REC_THREADS 128          /* dense form: one thread per bitmap word, a block covers 128*512 B = 64 KiB of text */
+
+struct RecParams {
+	const uint8_t  *text;
+	const uint32_t *bitmap;      /* NULL: every chunk flagged */
+	uint64_t n, n_chunks, n_words;
+	const agb_desc *desc;        /* device copy */
+	uint32_t *tile_counts;       /* dense: per block; list: per candidate */
+	const uint64_t *tile_offsets;/* exclusive scan of tile_counts (emit pass) */
+	agb_record *records; uint64_t capacity;
+	unsigned long long *totals;  /* [0] matched, [1] flagged chunks, [2..10] level histogram, [12] candidates in the list */
+	const uint64_t *cand; uint64_t cand_cap;   /* list form: ordered flagged chunk numbers, totals[12] of them */
+	int emit;                    /* 0: count pass, 1: emit pass */
+	int levels;                  /* 1: best-match bookkeeping (smallest matching row) */
+	int want_level;              /* levels: report records whose smallest level <= want_level (-1: all matching) */
+};
+
+/* The records chunk c owns: a record [s-1, close) belongs to the FIRST flagged chunk that meets it, so
+ *   (a) the record that contains byte 16c is ours iff its re-fed byte s-1 lies after the previous flagged chunk
+ *       (search backwards, stop at a delimiter end -> ours, or at a flagged chunk -> theirs);
+ *   (b) every record whose re-fed byte lies inside the chunk is ours.
+ * done_until (dense form) remembers how far this thread's previous chunk already got.
+ * Returns the number of reported records; writes them at out_pos.. when write is set. */
+template <typename T, int NR, bool COSTS>
+__device__ __forceinline__ uint32_t chunk_records(const RecParams &P, const DevConsts<T> &C, RecShared<T, NR> &SH, Reader &R,
+                                                 const int64_t c, int64_t &done_until, const bool write, const uint64_t out_pos, const bool hist)
 {
-	__shared__ unsigned long long part[1024];
-	const uint64_t per = (n_tiles + 1023) / 1024, a = threadIdx.x * per, b = (a + per < n_tiles) ? a + per : n_tiles;
-	unsigned long long s = 0;
-	for (uint64_t i = a; i < b; i++) s += counts[i];
-	part[threadIdx.x] = s;
-	__syncthreads();
-	for (int off = 1; off < 1024; off <<= 1) {
-		unsigned long long v = (threadIdx.x >= (unsigned)off) ? part[threadIdx.x - off] : 0;
+	const int L = C.L;
+	const int64_t n = (int64_t)P.n, lo = c * 16, hi = lo + 15;
+	uint32_t cnt = 0;
+	int64_t s = -2;                /* record start to run from; -2: none */
+	if (done_until > lo) {
+		/* the record this thread closed last reaches into this chunk; what starts here starts at done_until */
+		if (done_until - 1 <= hi) s = done_until; else return 0;
+	} else {
+		bool found = false;
+		if (c == 0) { s = 0; found = true; }
+		for (int64_t cc = c - 1; !found; cc--) {
+			if (cc < 0) { s = 0; found = true; break; }
+			uint32_t pw = P.bitmap ? P.bitmap[cc >> 5] : 0xffffffffu;
+			if (pw >> (cc & 31) & 1u) break;                  /* an earlier flagged chunk meets that record: not ours */
+			for (int64_t q = cc * 16 + 15; q >= cc * 16; q--)
+				if (delim_ends_at(R, q, SH.delim, L, C.kind)) { s = q + 1; found = true; break; }
+		}
+		if (!found) {
+			for (int64_t q = lo; q <= hi && q < n; q++)
+				if (delim_ends_at(R, q, SH.delim, L, C.kind)) { s = q + 1; break; }
+		}
+	}
+	/* run records while their re-fed byte (s-1) is at or before the end of this chunk */
+	while (s >= 0 && s - 1 <= hi && s <= n) {
+		T S[NR];
+		int64_t begin;
+		if (s == 0) {
+#pragma unroll
+			for (int r = 0; r < NR; r++) S[r] = SH.start[r];
+			begin = SH.start_closes ? -(int64_t)L : 0;
+		} else {
+#pragma unroll
+			for (int r = 0; r < NR; r++) S[r] = SH.reset[r];
+			begin = s - L;
+		}
+		int64_t p = s, close_at = -1;
+		const int64_t limit = n + L;
+		for (; p < limit; p++) {
+			rows_step<T, NR, COSTS>(S, SH.mask[R.get(p)], C);
+			if (S[0] & C.dendpos) { close_at = p; break; }
+		}
+		if (close_at < 0) { done_until = limit + 1; break; }           /* never closed: dropped, as the reference does */
+		const int64_t end = close_at + 1 - L;
+		const bool counts = (begin + 1 < n) && (begin + 1 <= end);       /* bitap.c:213 + agrep.c:3811 */
+		int level = C.k;
+		bool cond;
+		if (P.levels) {
+			level = -1;
+#pragma unroll
+			for (int r = 0; r < NR; r++) if (level < 0 && match_cond<T>(S[r], C)) level = r;
+			cond = level >= 0;
+			if (cond && counts && hist) atomicAdd(&SH.hist[level], 1ull);
+			if (cond && P.want_level >= 0 && level > P.want_level) cond = false;
+		} else cond = match_cond<T>(S[NR - 1], C);
+		if (cond && counts) {
+			if (write) {
+				const uint64_t at = out_pos + cnt;
+				if (at < P.capacity) {
+					agb_record rec; rec.begin = begin; rec.end = end; rec.ordinal = 0; rec.level = level; rec.pad = 0;
+					P.records[at] = rec;
+				}
+			}
+			cnt++;
+		}
+		s = close_at + 1;
+		done_until = s;
+	}
+	return cnt;
+}
+
+/* dense form: every thread owns one bitmap word (32 chunks); used when the plan flags everything or stage 1.5
+ * cannot thin the bitmap.  Count pass -> per-tile counts; emit pass recounts, scans inside the block, writes. */
+template <typename T, int NR, bool COSTS>
+__global__ void __launch_bounds__(REC_THREADS)
+k_records(const RecParams P)
+{
+	__shared__ RecShared<T, NR> SH;
+	__shared__ uint32_t s_scan[REC_THREADS];
+	DevConsts<T> C;
+	shared_init<T, NR>(SH, C, P.desc, REC_THREADS);
+	const uint64_t gw = (uint64_t)blockIdx.x * REC_THREADS + threadIdx.x;     /* bitmap word of this thread */
+	uint32_t word = 0;
+	if (gw < P.n_words) {
+		word = P.bitmap ? P.bitmap[gw] : 0xffffffffu;
+		uint64_t rem = P.n_chunks - gw * 32;
+		if (rem < 32) word &= (1u << rem) - 1u;
+	}
+	Reader R; R.init(P.text, P.n, SH.delim, C.L);
+	uint32_t my_count = 0;
+	uint64_t out_pos = 0;
+	for (int pass = 0; pass < (P.emit ? 2 : 1); pass++) {
+		uint32_t bits = word, cnt = 0;
+		int64_t done_until = INT64_MIN;
+		while (bits) {
+			const int b = __ffs(bits) - 1; bits &= bits - 1;
+			cnt += chunk_records<T, NR, COSTS>(P, C, SH, R, (int64_t)(gw * 32 + b), done_until, pass == 1, out_pos + cnt, pass == 0 && !P.emit);
+		}
+		if (pass == 0) {
+			my_count = cnt;
+			s_scan[threadIdx.x] = cnt;
+			__syncthreads();
+			for (int off = 1; off < REC_THREADS; off <<= 1) {
+				uint32_t v = (threadIdx.x >= (unsigned)off) ? s_scan[threadIdx.x - off] : 0;
+				__syncthreads();
+				s_scan[threadIdx.x] += v;
+				__syncthreads();
+			}
+			if (!P.emit) {
+				if (threadIdx.x == REC_THREADS - 1) {
+					P.tile_counts[blockIdx.x] = s_scan[REC_THREADS - 1];
+					if (s_scan[REC_THREADS - 1]) atomicAdd(&P.totals[0], (unsigned long long)s_scan[REC_THREADS - 1]);
+				}
+				uint32_t fl = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(word));
+				if ((threadIdx.x & 31) == 0 && fl) atomicAdd(&P.totals[1], (unsigned long long)fl);
+				__syncthreads();
+				if (P.levels && threadIdx.x <= AGB_MAXERR && SH.hist[threadIdx.x]) atomicAdd(&P.totals[2 + threadIdx.x], SH.hist[threadIdx.x]);
+			} else {
+				out_pos = P.tile_offsets[blockIdx.x] + (s_scan[threadIdx.x] - my_count);
+			}
+		}
+	}
+}
+
+/* list form: one thread per surviving chunk of the ordered candidate list (all lanes busy however sparse the
+ * survivors are).  Count launch: per-candidate counts; emit launch: writes at the scanned offsets. */
+template <typename T, int NR, bool COSTS>
+__global__ void __launch_bounds__(REC_THREADS)
+k_records_list(const RecParams P)
+{
+	__shared__ RecShared<T, NR> SH;
+	DevConsts<T> C;
+	shared_init<T, NR>(SH, C, P.desc, REC_THREADS);
+	unsigned long long ncand = P.totals[12];
+	if (ncand > P.cand_cap) ncand = P.cand_cap;
+	const uint64_t i = (uint64_t)blockIdx.x * REC_THREADS + threadIdx.x;
+	uint32_t cnt = 0;
+	if (i < ncand) {
+		Reader R; R.init(P.text, P.n, SH.delim, C.L);
+		int64_t done_until = INT64_MIN;
+		cnt = chunk_records<T, NR, COSTS>(P, C, SH, R, (int64_t)P.cand[i], done_until, P.emit != 0, P.emit ? P.tile_offsets[i] : 0, !P.emit);
+		if (!P.emit) P.tile_counts[i] = cnt;
+	}
+	if (!P.emit) {
+		uint32_t sum = __reduce_add_sync(0xffffffffu, cnt);
+		if ((threadIdx.x & 31) == 0 && sum) atomicAdd(&P.totals[0], (unsigned long long)sum);
 		__syncthreads();
-		part[threadIdx.x] += v;
+		if (P.levels && threadIdx.x <= AGB_MAXERR && SH.hist[threadIdx.x]) atomicAdd(&P.totals[2 + threadIdx.x], SH.hist[threadIdx.x]);
+	}
+}
+
+/* bitmap -> ordered list of flagged chunk numbers: per-block popcounts, scan (k_scan_tiles), scatter */
+#define COMPACT_THREADS 256
+#define COMPACT_WPT 4            /* words per thread: a block covers 1024 words */
+__global__ void __launch_bounds__(COMPACT_THREADS) k_compact_count(const uint32_t *bitmap, uint64_t n_words, uint32_t *block_counts, unsigned long long *totals)
+{
+	const uint64_t w0 = ((uint64_t)blockIdx.x * COMPACT_THREADS + threadIdx.x) * COMPACT_WPT;
+	uint32_t c = 0;
+#pragma unroll
+	for (int j = 0; j < COMPACT_WPT; j++) if (w0 + j < n_words) c += __popc(bitmap[w0 + j]);
+	__shared__ uint32_t s_part[COMPACT_THREADS / 32];
+	uint32_t sum = __reduce_add_sync(0xffffffffu, c);
+	if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = sum;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t t = 0;
+		for (int j = 0; j < COMPACT_THREADS / 32; j++) t += s_part[j];
+		block_counts[blockIdx.x] = t;
+		if (t) atomicAdd(&totals[1], (unsigned long long)t);
+	}
+}
+
+__global__ void __launch_bounds__(COMPACT_THREADS) k_compact_write(const uint32_t *bitmap, uint64_t n_words, const uint64_t *block_offsets,
+                                                                   uint64_t *list, uint64_t cap)
+{
+	const uint64_t w0 = ((uint64_t)blockIdx.x * COMPACT_THREADS + threadIdx.x) * COMPACT_WPT;
+	uint32_t wd[COMPACT_WPT], c = 0;
+#pragma unroll
+	for (int j = 0; j < COMPACT_WPT; j++) { wd[j] = (w0 + j < n_words) ? bitmap[w0 + j] : 0u; c += __popc(wd[j]); }
+	__shared__ uint32_t s_scan[COMPACT_THREADS];
+	s_scan[threadIdx.x] = c;
+	__syncthreads();
+	for (int off = 1; off < COMPACT_THREADS; off <<= 1) {
+		uint32_t v = (threadIdx.x >= (unsigned)off) ? s_scan[threadIdx.x - off] : 0;
+		__syncthreads();
+		s_scan[threadIdx.x] += v;
 		__syncthreads();
 	}
-	unsigned long long run = part[threadIdx.x] - s;
-	for (uint64_t i = a; i < b; i++) { offsets[i] = run; run += counts[i]; }
+	uint64_t at = block_offsets[blockIdx.x] + (s_scan[threadIdx.x] - c);
+#pragma unroll
+	for (int j = 0; j < COMPACT_WPT; j++)
+		for (uint32_t b = wd[j]; b; b &= b - 1) { if (at < cap) list[at] = (w0 + j) * 32 + (uint64_t)(__ffs(b) - 1); at++; }
+}
+
+/* exclusive scan of 32-bit counts into 64-bit offsets (one block, coalesced tiles of 4096 with a running carry);
+ * the grand total goes to *total when given */
+__global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *counts, uint64_t *offsets, uint64_t n_tiles, unsigned long long *total)
+{
+	__shared__ unsigned long long s_warp[32];
+	__shared__ unsigned long long s_carry;
+	const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	if (tid == 0) s_carry = 0;
+	__syncthreads();
+	for (uint64_t base = 0; base < n_tiles; base += 4096) {
+		uint32_t v[4]; unsigned long long sum = 0;
+#pragma unroll
+		for (int j = 0; j < 4; j++) { const uint64_t i = base + (uint64_t)tid * 4 + j; v[j] = i < n_tiles ? counts[i] : 0u; sum += v[j]; }
+		unsigned long long inc = sum;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (uint32_t)o) inc += t; }
+		if (lane == 31) s_warp[wid] = inc;
+		__syncthreads();
+		if (wid == 0) {
+			unsigned long long w = s_warp[lane], winc = w;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= (uint32_t)o) winc += t; }
+			s_warp[lane] = winc - w;                 /* exclusive prefix of the warp sums */
+		}
+		__syncthreads();
+		unsigned long long run = s_carry + s_warp[wid] + (inc - sum);
+#pragma unroll
+		for (int j = 0; j < 4; j++) { const uint64_t i = base + (uint64_t)tid * 4 + j; if (i < n_tiles) offsets[i] = run; run += v[j]; }
+		__syncthreads();
+		if (tid == 1023) s_carry = run;
+		__syncthreads();
+	}
+	if (total && tid == 0) *total = s_carry;
 }
 
 /* ================================================================================================
@@ -593,6 +744,7 @@ extern "C" int agb_corpus_fill_host(const agb_corpus_spec *s, void *h_text)
 struct Workspace {               /* grow-only device scratch, one per device */
 	uint32_t *bitmap = nullptr; size_t bitmap_bytes = 0;
 	uint32_t *tile_counts = nullptr; uint64_t *tile_offsets = nullptr; size_t tiles = 0;
+	uint64_t *cand = nullptr; uint32_t *cand_counts = nullptr; uint64_t *cand_offsets = nullptr; size_t cand_cap = 0;
 	unsigned long long *totals = nullptr;          /* 16 counters */
 	unsigned long long *h_totals = nullptr;        /* pinned */
 	agb_desc *d_desc = nullptr; agb_desc h_desc_copy; bool desc_valid = false;
@@ -632,6 +784,17 @@ static int ws_prepare(Workspace &W, uint64_t n)
 		CUDA_TRY(cudaMalloc(&W.tile_counts, (tiles + 1) * sizeof(uint32_t)));
 		CUDA_TRY(cudaMalloc(&W.tile_offsets, (tiles + 1) * sizeof(uint64_t)));
 		W.tiles = tiles + 1;
+	}
+	size_t want_cand = std::max<size_t>((size_t)1 << 20, (size_t)(n_chunks / 128));
+	if (want_cand > W.cand_cap) {
+		if (W.cand) cudaFree(W.cand);
+		if (W.cand_counts) cudaFree(W.cand_counts);
+		if (W.cand_offsets) cudaFree(W.cand_offsets);
+		W.cand = nullptr; W.cand_counts = nullptr; W.cand_offsets = nullptr; W.cand_cap = 0;
+		CUDA_TRY(cudaMalloc(&W.cand, want_cand * sizeof(uint64_t)));
+		CUDA_TRY(cudaMalloc(&W.cand_counts, want_cand * sizeof(uint32_t)));
+		CUDA_TRY(cudaMalloc(&W.cand_offsets, want_cand * sizeof(uint64_t)));
+		W.cand_cap = want_cand;
 	}
 	return AGB_OK;
 }
@@ -770,12 +933,26 @@ static int launch_refine_t(int nrows, const RefineParams &P, unsigned grid, cuda
 	return 0;
 }
 
-/* stage 1.5 over the whole bitmap (only when the plan allows a purely local check) */
+/* can stage 1.5 judge this plan?  (single pattern without '#', windows that fit the staging area) */
+static bool refine_geometry(const agb_desc &d, RefineParams &P)
+{
+	if (!front_usable(d) || !d.refine) return false;
+	int max_off = 0, min_off = 1 << 30;
+	for (int i = 0; i < d.n_anchors; i++) { max_off = std::max(max_off, (int)d.anchor_off[i]); min_off = std::min(min_off, (int)d.anchor_off[i]); }
+	P.lo_off = max_off + d.k;
+	P.hi_off = 15 + d.pat_len - min_off + d.k;
+	P.gb = (P.lo_off + 15) / 16;
+	P.ng = P.gb + (P.hi_off + 15) / 16;
+	if (P.ng < P.gb + 2) P.ng = P.gb + 2;              /* the chunk itself and the word that follows it */
+	return P.ng <= REFINE_MAXG && max_off <= 31;
+}
+
+/* stage 1.5 over the whole bitmap */
 static int refine_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, cudaStream_t st)
 {
-	if (!front_usable(d) || !d.refine || n == 0) return AGB_OK;
-	const uint64_t n_chunks = (n + 15) / 16, n_words = (n_chunks + 31) / 32;
 	RefineParams P; memset(&P, 0, sizeof P);
+	if (n == 0 || !refine_geometry(d, P)) return AGB_OK;
+	const uint64_t n_chunks = (n + 15) / 16, n_words = (n_chunks + 31) / 32;
 	P.text = (const uint8_t *)d_text; P.bitmap = W.bitmap; P.n = n; P.n_chunks = n_chunks; P.n_words = n_words; P.desc = W.d_desc;
 	P.fold = d.anchor_fold; P.amask = d.anchor_mask; P.na = d.n_anchors;
 	for (int i = 0; i < d.n_anchors; i++) { P.anchor[i] = d.anchor[i]; P.off[i] = d.anchor_off[i]; }
@@ -790,7 +967,35 @@ static int refine_launch(const agb_desc &d, Workspace &W, const void *d_text, ui
 	return AGB_OK;
 }
 
-/* stage 2 (+ tile scan + emit pass when a list is wanted) over the whole text */
+template <typename T, bool COSTS>
+static int launch_records_list_t(int nrows, const RecParams &P, unsigned grid, cudaStream_t st)
+{
+	switch (nrows) {
+	case 1: k_records_list<T, 1, COSTS><<<grid, REC_THREADS, 0, st>>>(P); break;
+	case 2: k_records_list<T, 2, COSTS><<<grid, REC_THREADS, 0, st>>>(P); break;
+	case 3: k_records_list<T, 3, COSTS><<<grid, REC_THREADS, 0, st>>>(P); break;
+	case 4: k_records_list<T, 4, COSTS><<<grid, REC_THREADS, 0, st>>>(P); break;
+	case 5: k_records_list<T, 5, COSTS><<<grid, REC_THREADS, 0, st>>>(P); break;
+	case 6: k_records_list<T, 6, COSTS><<<grid, REC_THREADS, 0, st>>>(P); break;
+	case 7: k_records_list<T, 7, COSTS><<<grid, REC_THREADS, 0, st>>>(P); break;
+	case 8: k_records_list<T, 8, COSTS><<<grid, REC_THREADS, 0, st>>>(P); break;
+	case 9: k_records_list<T, 9, COSTS><<<grid, REC_THREADS, 0, st>>>(P); break;
+	default: return -1;
+	}
+	g_launches++;
+	return 0;
+}
+
+static int launch_records_list(const agb_desc &d, const RecParams &P, unsigned grid, cudaStream_t st)
+{
+	const bool costs = d.engine == AGB_ENGINE_ASEARCH1, narrow = d.M <= 31;
+	if (costs) return narrow ? launch_records_list_t<uint32_t, true>(d.nrows, P, grid, st) : launch_records_list_t<uint64_t, true>(d.nrows, P, grid, st);
+	return narrow ? launch_records_list_t<uint32_t, false>(d.nrows, P, grid, st) : launch_records_list_t<uint64_t, false>(d.nrows, P, grid, st);
+}
+
+/* stage 2 over the whole text.  After stage 1.5 the survivors are few: they are compacted into an ordered list
+ * and each gets its own thread (count launch -> scan -> emit launch).  Otherwise (or if the list would not fit)
+ * the dense form walks the bitmap, one thread per word. */
 static int records_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, bool use_front, int want,
                           int want_level, agb_record *d_records, uint64_t capacity, cudaStream_t st)
 {
@@ -798,13 +1003,41 @@ static int records_launch(const agb_desc &d, Workspace &W, const void *d_text, u
 	RecParams P; memset(&P, 0, sizeof P);
 	P.text = (const uint8_t *)d_text; P.bitmap = use_front ? W.bitmap : nullptr;
 	P.n = n; P.n_chunks = n_chunks; P.n_words = n_words; P.desc = W.d_desc;
-	P.tile_counts = W.tile_counts; P.tile_offsets = W.tile_offsets; P.records = d_records; P.capacity = capacity;
+	P.records = d_records; P.capacity = capacity;
 	P.totals = W.totals; P.emit = 0; P.levels = (want & AGB_WANT_LEVELS) ? 1 : 0; P.want_level = want_level;
 	if (!tiles) return AGB_OK;
+	const bool want_list = (want & AGB_WANT_RECORDS) && capacity;
+	RefineParams geo; memset(&geo, 0, sizeof geo);
+	if (use_front && refine_geometry(d, geo)) {
+		const uint64_t blocks = (n_words + COMPACT_THREADS * COMPACT_WPT - 1) / (COMPACT_THREADS * COMPACT_WPT);
+		k_compact_count<<<(unsigned)blocks, COMPACT_THREADS, 0, st>>>(W.bitmap, n_words, W.tile_counts, W.totals); g_launches++;
+		k_scan_tiles<<<1, 1024, 0, st>>>(W.tile_counts, W.tile_offsets, blocks, W.totals + 12); g_launches++;
+		CUDA_TRY(cudaMemcpyAsync(W.h_totals + 12, W.totals + 12, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+		const unsigned long long ncand = W.h_totals[12];
+		if (ncand <= W.cand_cap) {
+			if (ncand == 0) return AGB_OK;
+			k_compact_write<<<(unsigned)blocks, COMPACT_THREADS, 0, st>>>(W.bitmap, n_words, W.tile_offsets, W.cand, W.cand_cap); g_launches++;
+			P.cand = W.cand; P.cand_cap = W.cand_cap; P.tile_counts = W.cand_counts; P.tile_offsets = W.cand_offsets;
+			const unsigned grid = (unsigned)((ncand + REC_THREADS - 1) / REC_THREADS);
+			if (launch_records_list(d, P, grid, st)) return AGB_ERR_ARG;
+			CUDA_TRY(cudaGetLastError());
+			if (want_list) {
+				k_scan_tiles<<<1, 1024, 0, st>>>(W.cand_counts, W.cand_offsets, ncand, nullptr); g_launches++;
+				P.emit = 1;
+				if (launch_records_list(d, P, grid, st)) return AGB_ERR_ARG;
+				CUDA_TRY(cudaGetLastError());
+			}
+			return AGB_OK;
+		}
+		/* too many survivors for the list: dense form below (totals[1] is recounted there) */
+		CUDA_TRY(cudaMemsetAsync(W.totals + 1, 0, sizeof(unsigned long long), st));
+	}
+	P.tile_counts = W.tile_counts; P.tile_offsets = W.tile_offsets;
 	if (launch_records(d, P, (unsigned)tiles, st)) return AGB_ERR_ARG;
 	CUDA_TRY(cudaGetLastError());
-	if ((want & AGB_WANT_RECORDS) && capacity) {
-		k_scan_tiles<<<1, 1024, 0, st>>>(W.tile_counts, W.tile_offsets, tiles); g_launches++;
+	if (want_list) {
+		k_scan_tiles<<<1, 1024, 0, st>>>(W.tile_counts, W.tile_offsets, tiles, nullptr); g_launches++;
 		P.emit = 1;
 		if (launch_records(d, P, (unsigned)tiles, st)) return AGB_ERR_ARG;
 		CUDA_TRY(cudaGetLastError());
@@ -870,16 +1103,20 @@ static void par_memcpy(uint8_t *dst, const uint8_t *src, size_t len)
 }
 
 /* Host text -> HBM -> scan: the replacement of the fill_buf()/read(2) loop (bitap.c:143,450-477).  The text is
- * moved in 64 MiB slices on a copy stream (straight from the caller's memory when it is page-locked, else
- * through a pinned ring filled by 4 host threads) while stage 1 runs on the slice that arrived before, so
- * the scan hides behind PCIe; stage 2 runs once over the whole bitmap. */
-extern "C" int agb_scan_host(const agb_pattern *p, const void *h_text, uint64_t n, int want,
-                             agb_record *records, uint64_t capacity, agb_result *res)
+ * moved in 64 MiB slices on a copy stream -- straight from the caller's memory when it is page-locked; through a
+ * pinned ring filled by 4 host threads when it is pageable; read(2) straight into the pinned ring when the
+ * source is a file descriptor -- while stage 1 runs on the slice that arrived before (its last chunk looks 4
+ * bytes into the next one), so the scan hides behind PCIe; stages 1.5 and 2 run once over the whole bitmap. */
+struct SliceSource {
+	const uint8_t *mem;      /* host memory source, or NULL */
+	bool pinned;             /* mem is page-locked: copy from it directly */
+	int fd;                  /* file descriptor source when mem == NULL */
+};
+
+static int scan_stream_impl(const agb_desc &d, uint64_t n, const SliceSource &src, int want,
+                            agb_record *records, uint64_t capacity, agb_result *res)
 {
-	if (!p || !res || (!h_text && n)) return AGB_ERR_ARG;
-	if ((want & AGB_WANT_RECORDS) && capacity && !records) return AGB_ERR_ARG;
 	memset(res, 0, sizeof *res);
-	const agb_desc &d = p->d;
 	int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
 	if (dev < 0 || dev >= 64) return AGB_ERR_ARG;
 	std::lock_guard<std::mutex> lk(g_ws_mu);
@@ -902,10 +1139,8 @@ extern "C" int agb_scan_host(const agb_pattern *p, const void *h_text, uint64_t 
 		CUDA_TRY(cudaMalloc(&W.h2d_rec, capacity * sizeof(agb_record))); W.h2d_rec_cap = capacity;
 	}
 	rc = ws_upload_desc(W, d, W.s_comp); if (rc) return rc;
-	cudaPointerAttributes attr; memset(&attr, 0, sizeof attr);
-	bool pinned = n && cudaPointerGetAttributes(&attr, h_text) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-	cudaGetLastError();
-	if (!pinned && n && !W.stage[0]) for (int i = 0; i < STAGE_BUFS; i++) CUDA_TRY(cudaMallocHost(&W.stage[i], H2D_SLICE));
+	const bool direct = src.mem && src.pinned;
+	if (!direct && n && !W.stage[0]) for (int i = 0; i < STAGE_BUFS; i++) CUDA_TRY(cudaMallocHost(&W.stage[i], H2D_SLICE));
 	const bool use_front = front_usable(d) && n > 0;
 	const uint64_t words_per_slice = H2D_SLICE / 512, n_slices = (n + H2D_SLICE - 1) / H2D_SLICE;
 	CUDA_TRY(cudaMemsetAsync(W.totals, 0, 16 * sizeof(unsigned long long), W.s_comp));
@@ -915,11 +1150,19 @@ extern "C" int agb_scan_host(const agb_pattern *p, const void *h_text, uint64_t 
 	for (uint64_t i = 0; i < n_slices; i++) {
 		const uint64_t off = i * H2D_SLICE, len = std::min<uint64_t>(H2D_SLICE, n - off);
 		const int sb = (int)(i % STAGE_BUFS);
-		if (pinned) {
-			CUDA_TRY(cudaMemcpyAsync(W.h2d_text + off, (const uint8_t *)h_text + off, len, cudaMemcpyHostToDevice, W.s_copy));
+		if (direct) {
+			CUDA_TRY(cudaMemcpyAsync(W.h2d_text + off, src.mem + off, len, cudaMemcpyHostToDevice, W.s_copy));
 		} else {
 			if (i >= STAGE_BUFS) CUDA_TRY(cudaEventSynchronize(W.ev_copy[sb]));     /* that staging buffer has been consumed */
-			par_memcpy(W.stage[sb], (const uint8_t *)h_text + off, len);
+			if (src.mem) par_memcpy(W.stage[sb], src.mem + off, len);
+			else {
+				uint64_t got = 0;                                                   /* fill_buf(): read(2) until the slice is full */
+				while (got < len) {
+					ssize_t r = read(src.fd, W.stage[sb] + got, (size_t)(len - got));
+					if (r <= 0) { snprintf(g_err, sizeof g_err, "read(2) returned %zd at offset %llu of %llu", r, (unsigned long long)(off + got), (unsigned long long)n); return AGB_ERR_ARG; }
+					got += (uint64_t)r;
+				}
+			}
 			CUDA_TRY(cudaMemcpyAsync(W.h2d_text + off, W.stage[sb], len, cudaMemcpyHostToDevice, W.s_copy));
 		}
 		CUDA_TRY(cudaEventRecord(W.ev_copy[sb], W.s_copy));
@@ -948,9 +1191,33 @@ extern "C" int agb_scan_host(const agb_pattern *p, const void *h_text, uint64_t 
 	return AGB_OK;
 }
 
+extern "C" int agb_scan_host(const agb_pattern *p, const void *h_text, uint64_t n, int want,
+                             agb_record *records, uint64_t capacity, agb_result *res)
+{
+	if (!p || !res || (!h_text && n)) return AGB_ERR_ARG;
+	if ((want & AGB_WANT_RECORDS) && capacity && !records) return AGB_ERR_ARG;
+	SliceSource src; src.mem = (const uint8_t *)h_text; src.fd = -1; src.pinned = false;
+	if (n) {
+		cudaPointerAttributes attr; memset(&attr, 0, sizeof attr);
+		src.pinned = cudaPointerGetAttributes(&attr, h_text) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+		cudaGetLastError();
+	}
+	return scan_stream_impl(p->d, n, src, want, records, capacity, res);
+}
+
 extern "C" int agb_scan_fd(const agb_pattern *p, int fd, int want, agb_record *records, uint64_t capacity, agb_result *res)
 {
-	/* fill_buf() (bitap.c:450-477): read(2) until EOF; here into one growing host buffer, then agb_scan_host */
+	if (!p || !res) return AGB_ERR_ARG;
+	if ((want & AGB_WANT_RECORDS) && capacity && !records) return AGB_ERR_ARG;
+	struct stat sb;
+	if (fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode)) {
+		/* regular file: the size is known, read(2) goes straight into the pinned ring, slice by slice */
+		off_t cur = lseek(fd, 0, SEEK_CUR);
+		uint64_t n = (cur >= 0 && sb.st_size > cur) ? (uint64_t)(sb.st_size - cur) : 0;
+		SliceSource src; src.mem = nullptr; src.pinned = false; src.fd = fd;
+		return scan_stream_impl(p->d, n, src, want, records, capacity, res);
+	}
+	/* pipes, ttys: fill_buf() semantics -- read until EOF into a growing buffer, then as host memory */
 	size_t cap = 1 << 20, len = 0; uint8_t *buf = (uint8_t *)malloc(cap);
 	if (!buf) return AGB_ERR_NOMEM;
 	for (;;) {

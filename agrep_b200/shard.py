@@ -1,0 +1,76 @@
+"""Multi-GPU host logic: shard a text by byte range at record boundaries, gather the per-shard match lists.
+
+Records are independent once their boundaries are known (the automaton is reset at every delimiter,
+asearch.c:175-196), so the scan path needs no data-path collective: rank r scans [cut[r], cut[r+1]) as a text
+of its own and only the match lists travel.  The cut rule: the nominal cut i*n/world moves forward
+to just after the first delimiter that ENDS at or after it; for run delimiters ($$ = "\\n\\n") the greedy,
+non-overlapping parse is resolved from the start of the run, exactly as the device does (scan.cu delim_ends_at).
+A shard therefore starts where a record starts and its scan begins with the same virtual '\\n' the reference
+puts in front of a file (bitap.c:140) -- which is also what precedes the record in the whole text whenever the
+delimiter ends in '\\n'.  (For delimiters not ending in '\\n' the first record of a shard sees '\\n' instead of
+the delimiter's last byte as its re-fed byte; -w patterns can tell the two apart, so such texts are cut only
+where the re-fed byte is irrelevant -- see `cut_points(..., strict=True)`.)
+"""
+import torch
+
+
+def _delim_ends_at(text, q, delim):
+    """is q the last byte of a record-closing delimiter (same rule as the device, scan.cu)?"""
+    L = len(delim)
+    if L == 1:
+        return text[q] == delim[0]
+    if any(delim[:b] == delim[L - b:] for b in range(1, L)):          # self-overlapping: only runs c^L are supported
+        c = delim[0]
+        if text[q] != c:
+            return False
+        run, p = 1, q - 1
+        while p >= 0 and text[p] == c:
+            run += 1
+            p -= 1
+        if p < 0 and c == 0x0A:
+            run += 1                                                    # the virtual '\n' in front of the text
+        return run % L == 0
+    return q + 1 >= L and bytes(text[q + 1 - L:q + 1]) == bytes(delim)
+
+
+def cut_points(text, world, delim=b"\n"):
+    """[0, c1, ..., n]: shard r is text[c[r]:c[r+1]]; every interior cut is the first byte after a delimiter."""
+    n = len(text)
+    cuts = [0]
+    for r in range(1, world):
+        q = max(cuts[-1], (n * r) // world)
+        while q < n and not _delim_ends_at(text, q, delim):
+            q += 1
+        cuts.append(min(q + 1, n))
+    cuts.append(n)
+    return cuts
+
+
+def page_shards(total_bytes, world, page=4096):
+    """synthetic corpus: records never cross a 4 KiB page, so equal page-aligned ranges are record aligned"""
+    per = total_bytes // (page * world) * page
+    return [(r * per, per) for r in range(world)]
+
+
+def gather_records(recs, n_records, base, dist=None, group=None):
+    """recs: int64 tensor [cap, 4] of (begin, end, ordinal, level) with shard-local offsets, n_records valid rows.
+    Returns on every rank the concatenation over ranks, offsets made global (+ base) -- ordered because shards are.
+    Collectives: all_gather of the counts, all_gather of the lists padded to the longest (payload = 32 B/record)."""
+    blk = recs[:n_records].clone()
+    if n_records:
+        blk[:, 0:2] += base
+    if dist is None or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return blk
+    world = dist.get_world_size(group)
+    cnt = torch.tensor([n_records], dtype=torch.int64, device=recs.device)
+    allc = torch.zeros(world, dtype=torch.int64, device=recs.device)
+    dist.all_gather_into_tensor(allc, cnt, group=group)
+    counts = [int(x) for x in allc.tolist()]
+    m = max(counts)
+    if m == 0:
+        return blk
+    pad = torch.zeros((m, 4), dtype=torch.int64, device=recs.device)
+    pad[:n_records] = blk
+    out = torch.empty((world * m, 4), dtype=torch.int64, device=recs.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    return torch.cat([out[r * m:r * m + counts[r]] for r in range(world)], dim=0)

@@ -209,7 +209,7 @@ def main():
 
     import torch
     import agrep_b200 as ag
-    from agrep_b200 import _lib
+    from agrep_b200 import _lib, shard
     L = _lib.lib()                      # raises if the CUDA library is missing: there is no fallback
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -236,23 +236,14 @@ def main():
     pat = ag.Pattern(PATTERN, k=K)
     CAP = 1 << 22
     recs = torch.zeros((CAP, 4), dtype=torch.int64, device=dev)       # agb_record = 4 x int64 (level+pad packed in the last)
-    cnt_t = torch.zeros(1, dtype=torch.int64, device=dev)
-    all_cnt = torch.zeros(world, dtype=torch.int64, device=dev)
 
     def step():
         res = pat.scan_device(corpus.data_ptr(), n_local, stream=stream, d_records=recs.data_ptr(), capacity=CAP)
         gathered = res.n_records
         if world > 1:
-            # shard-local offsets -> corpus offsets, then NCCL gather of the variable-length lists (padded to the max)
-            cnt_t[0] = res.n_records
-            dist.all_gather_into_tensor(all_cnt, cnt_t)
-            m = int(all_cnt.max().item())
-            if m:
-                blk = recs[:m].clone()
-                blk[:res.n_records, 0:2] += rank * n_local
-                out = torch.empty((world * m, 4), dtype=torch.int64, device=dev)
-                dist.all_gather_into_tensor(out, blk)
-            gathered = int(all_cnt.sum().item())
+            # shard-local offsets -> corpus offsets, then NCCL: all_gather of the counts + all_gather of the padded lists
+            allr = shard.gather_records(recs, int(res.n_records), rank * n_local, dist)
+            gathered = int(allr.shape[0])
         return res, gathered
 
     for _ in range(args.warmup):

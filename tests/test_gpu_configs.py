@@ -1,0 +1,50 @@
+"""BASELINE.json configs[2] and configs[3] as parity cases:
+  configs[2]: 32-char pattern, -3 -w, paragraph records (-d '$$'): M = 37 > 32, the reference refuses it
+              ("pattern too long", maskgen.c:201-208), so parity is against the widened oracle (validated on M<=31
+              against the real reference in test_oracle_vs_reference.py); a 26-char variant the reference accepts is in the
+              golden vectors (para_k3_26).
+  configs[3]: -i -B best-match sweep with a 20-char mixed-case pattern (agrep.c:3582-3728)."""
+import pytest
+import _oracle
+import agrep_b200 as ag
+
+pytestmark = pytest.mark.gpu
+PAGE = 4096
+P32 = "business give group toward young"          # 32 chars, five adjacent vocabulary words
+P20 = "Because Each Just Th"                      # 20 chars, mixed case
+
+
+def test_config2_wide_pattern_paragraph_records():
+    assert len(P32) == 32
+    with pytest.raises(_oracle.OracleError):
+        _oracle.compile(P32, width=32, k=3, linenum=1, wordbound=1, delim="$$")      # the reference's own limit
+    n = 2048 * PAGE
+    host = ag.corpus_host(n, paragraphs=True, needle=P32, needle_every=16, needle_maxedits=4)
+    kw = dict(k=3, linenum=1, wordbound=1, delim="$$")
+    a = _oracle.compile(P32, **kw)
+    assert a.M == 37
+    cnt, recs = _oracle.scan(a, host)
+    p = ag.Pattern(P32, k=3, linenum=True, wordbound=True, delim="$$")
+    d = p.desc
+    assert d.M == 37 and d.plan == ag.api.PLAN_ANCHORS and d.n_anchors == 4
+    res, got = p.scan_host(host)
+    assert res.n_matched == cnt and cnt >= 60
+    assert [(b, e) for b, e, _, _ in got] == [(b, e) for b, e, _ in recs]
+
+
+def test_config3_bestmatch_sweep_case_insensitive():
+    import torch
+    n = 4096 * PAGE
+    for maxedits, every in ((0, 64), (3, 64), (2, 1 << 20)):
+        needle = "because each just th"
+        host = ag.corpus_host(n, needle=needle, needle_every=every, needle_maxedits=maxedits)
+        t = torch.frombuffer(bytearray(host + b"\0" * 64), dtype=torch.uint8).cuda()
+        want = -1
+        for k in range(0, 9):
+            a = _oracle.compile(P20, k=k, linenum=1, nocase=1)
+            cnt, _ = _oracle.scan(a, host, want_records=False)
+            if cnt:
+                want = (k, cnt)
+                break
+        best, res = ag.bestmatch_device(P20, t.data_ptr(), n, nocase=1)
+        assert (best, res.n_matched) == want, (maxedits, every, best, res.n_matched, want)

@@ -19,7 +19,8 @@ def files():
     d = tempfile.mkdtemp(prefix="agb_dropin_")
     paths = {}
     for name, data in (("a.txt", _corpus.make_text(3000, seed=11)), ("b.txt", _corpus.make_text(2000, seed=12, trailing_newline=False)),
-                       ("para.txt", _corpus.make_text(2500, seed=13, paragraphs=True))):
+                       ("para.txt", _corpus.make_text(2500, seed=13, paragraphs=True)),
+                       ("small.txt", _corpus.make_text(600, seed=14))):      # < 48 KiB: no block artefacts in -b
         paths[name] = os.path.join(d, name)
         open(paths[name], "wb").write(data)
     yield paths
@@ -50,7 +51,7 @@ CASES = [
     (["-c", "-n", "-v", "the"], ["a.txt"]),
     (["-n", "-w", "-1", "matching"], ["a.txt"]),
     (["-n", "st.t[a-e]"], ["a.txt"]),
-    (["-n", "-b", "-1", "homogeneous"], ["a.txt"]),
+    (["-n", "-b", "-1", "homogeneous"], ["small.txt"]),
     (["-n", "-d", "$$", "-1", "because each"], ["para.txt"]),    # paragraph records
     (["-c", "-n", "-d", "$$", "-w", "world"], ["para.txt"]),
     (["-n", "-y", "-B", "goverment of the peple"], ["a.txt"]),   # best-match sweep, no prompt

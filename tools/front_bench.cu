@@ -103,7 +103,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
 	asm volatile("{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@!p bra W_%=;\n}" :: "r"(smem_u32(b)), "r"(parity) : "memory"); }
 
-template <int NA, int NST, int T, int CH>
+template <int NA, int NST, int T, int CH, int XMODE>
 __global__ void __launch_bounds__(T) k_tma(const P p, uint64_t total_bytes_readable)
 {
 	extern __shared__ __align__(128) uint8_t smem[];
@@ -133,7 +133,10 @@ __global__ void __launch_bounds__(T) k_tma(const P p, uint64_t total_bytes_reada
 		for (int c = 0; c < CH; c++) {
 			uint32_t idx = c * T + tid;
 			uint4 v = *reinterpret_cast<const uint4 *>(st + idx * 16);
-			uint32_t x4 = *reinterpret_cast<const uint32_t *>(st + idx * 16 + 16);
+			uint32_t x4;
+			if (XMODE == 0) x4 = *reinterpret_cast<const uint32_t *>(st + idx * 16 + 16);
+			else if (XMODE == 1) { x4 = __shfl_down_sync(0xffffffffu, v.x, 1); if (lane == 31) x4 = *reinterpret_cast<const uint32_t *>(st + idx * 16 + 16); }
+			else { uint32_t a, b, c2, d; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c2), "=r"(d) : "r"(smem_u32(st + idx * 16 + 16))); x4 = a; }
 			uint32_t acc = 0xffffffffu;
 			acc = winpoly<NA, false>(v.x, v.y, p, acc); acc = winpoly<NA, false>(v.y, v.z, p, acc);
 			acc = winpoly<NA, false>(v.z, v.w, p, acc); acc = winpoly<NA, false>(v.w, x4, p, acc);
@@ -147,23 +150,23 @@ __global__ void __launch_bounds__(T) k_tma(const P p, uint64_t total_bytes_reada
 	}
 }
 
-template <int NA, int NST, int T, int CH>
+template <int NA, int NST, int T, int CH, int XMODE = 0>
 static void run_tma(const char *name, P p, uint64_t bytes, int sms, int bps)
 {
 	set_coef(p, NA);
 	cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
 	int smem = NST * (T * CH * 16 + 16);
-	CK(cudaFuncSetAttribute(k_tma<NA, NST, T, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+	CK(cudaFuncSetAttribute(k_tma<NA, NST, T, CH, XMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 	std::vector<float> ms;
 	for (int it = 0; it < 6; it++) {
 		CK(cudaEventRecord(e0));
-		k_tma<NA, NST, T, CH><<<sms * bps, T, smem>>>(p, bytes + 64);
+		k_tma<NA, NST, T, CH, XMODE><<<sms * bps, T, smem>>>(p, bytes + 64);
 		CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
 		float t; CK(cudaEventElapsedTime(&t, e0, e1)); if (it >= 2) ms.push_back(t);
 	}
 	CK(cudaGetLastError());
 	std::sort(ms.begin(), ms.end());
-	printf("%-28s NA=%d NST=%d T=%d CH=%d grid=%dx%d smem=%d  %8.3f ms  %8.1f GB/s\n", name, NA, NST, T, CH, sms, bps, smem, ms[0], bytes / ms[0] / 1e6);
+	printf("%-28s NA=%d NST=%d T=%d CH=%d X=%d grid=%dx%d smem=%d  %8.3f ms  %8.1f GB/s\n", name, NA, NST, T, CH, XMODE, sms, bps, smem, ms[0], bytes / ms[0] / 1e6);
 	fflush(stdout);
 }
 
@@ -218,6 +221,22 @@ int main(int argc, char **argv)
 	P p; p.text = (const uint4 *)text; p.bitmap = bitmap; p.n_chunks = bytes / 16; p.n_words = p.n_chunks / 32;
 	const char *a[8] = { "beca", "use ", "each", "gove", "rnme", "ntal", "xyzw", "qqqq" };
 	for (int i = 0; i < 8; i++) p.anchor[i] = *(const uint32_t *)a[i];
+	run_tma<3, 4, 256, 4, 0>("tma-poly", p, bytes, sms, 3);
+	run_tma<3, 4, 256, 4, 1>("tma-poly", p, bytes, sms, 3);
+	run_tma<3, 4, 256, 4, 2>("tma-poly", p, bytes, sms, 3);
+	run_tma<3, 3, 256, 4, 0>("tma-poly", p, bytes, sms, 4);
+	run_tma<3, 3, 256, 4, 2>("tma-poly", p, bytes, sms, 4);
+	run_tma<3, 2, 256, 4, 0>("tma-poly", p, bytes, sms, 6);
+	run_tma<3, 4, 256, 2, 0>("tma-poly", p, bytes, sms, 5);
+	run_tma<3, 8, 256, 2, 0>("tma-poly", p, bytes, sms, 3);
+	run_tma<3, 4, 384, 4, 0>("tma-poly", p, bytes, sms, 2);
+	run_tma<3, 4, 128, 8, 0>("tma-poly", p, bytes, sms, 3);
+	run_tma<3, 4, 128, 4, 0>("tma-poly", p, bytes, sms, 6);
+	run_tma<1, 4, 256, 4, 0>("tma-poly", p, bytes, sms, 3);
+	run_tma<2, 4, 256, 4, 0>("tma-poly", p, bytes, sms, 3);
+	run_tma<4, 4, 256, 4, 0>("tma-poly", p, bytes, sms, 3);
+	run_tma<5, 4, 256, 4, 0>("tma-poly", p, bytes, sms, 3);
+	return 0;
 	run_tma<1, 6, 256, 4>("tma-poly", p, bytes, sms, 2);
 	run_tma<3, 6, 256, 4>("tma-poly", p, bytes, sms, 2);
 	run_tma<3, 4, 256, 4>("tma-poly", p, bytes, sms, 3);
@@ -234,8 +253,8 @@ int main(int argc, char **argv)
 		k<5, 3, 4, 256><<<sms * 8, 256>>>(q); CK(cudaMemcpy(a.data(), bitmap, p.n_words * 4, cudaMemcpyDeviceToHost));
 		CK(cudaMemset(bitmap, 0xAA, p.n_words * 4));
 		int smem = 6 * (256 * 4 * 16 + 16);
-		CK(cudaFuncSetAttribute(k_tma<3, 6, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-		k_tma<3, 6, 256, 4><<<sms * 2, 256, smem>>>(q, bytes + 64); CK(cudaMemcpy(b.data(), bitmap, p.n_words * 4, cudaMemcpyDeviceToHost));
+		CK(cudaFuncSetAttribute(k_tma<3, 6, 256, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		k_tma<3, 6, 256, 4, 0><<<sms * 2, 256, smem>>>(q, bytes + 64); CK(cudaMemcpy(b.data(), bitmap, p.n_words * 4, cudaMemcpyDeviceToHost));
 		uint64_t diff = 0, set = 0; for (uint64_t i = 0; i < p.n_words; i++) { diff += a[i] != b[i]; set += __builtin_popcount(a[i]); }
 		printf("bitmap check: %llu differing words of %llu, %llu bits set\n", (unsigned long long)diff, (unsigned long long)p.n_words, (unsigned long long)set);
 	}
