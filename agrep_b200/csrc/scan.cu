@@ -566,6 +566,181 @@ k_records(const RecParams P)
 	}
 }
 
+/* dense tile form: the automaton over EVERYTHING (no anchor plan: classes, -v, -p, '#', short patterns ...).
+ * One CTA per 32 KiB tile.  The tile (+2 KiB that follow it) is brought into shared memory by one bulk-async
+ * copy; the threads find the record starts that lie in the tile (a delimiter ends just before them), the block
+ * orders them into a list, and every thread takes whole records from that list -- start state = the constant
+ * post-delimiter rows, text bytes from shared memory (global memory only for the rare record that outruns the
+ * staged bytes), exactly the loop of asearch.c:94-199 until the record closes.  A record belongs to the tile it
+ * starts in, so nothing is carried between tiles and the per-tile counts scan into an ordered global list. */
+#define DENSE_THREADS 256
+#define DENSE_TILE    32768
+#define DENSE_TAIL    2048
+#define DENSE_CAP     2048          /* record starts per round */
+
+template <typename T, int NR, bool COSTS>
+__global__ void __launch_bounds__(DENSE_THREADS)
+k_records_dense(const RecParams P)
+{
+	extern __shared__ __align__(128) uint8_t s_text[];                 /* DENSE_TILE + DENSE_TAIL */
+	__shared__ RecShared<T, NR> SH;
+	__shared__ uint64_t s_bar;
+	__shared__ uint16_t s_start[DENSE_CAP];
+	__shared__ unsigned long long s_close[DENSE_CAP];
+	__shared__ int8_t s_level[DENSE_CAP];                              /* -1: not reported */
+	__shared__ uint32_t s_scan[DENSE_THREADS];
+	__shared__ uint32_t s_total;
+	const uint32_t tid = threadIdx.x;
+	const int64_t n = (int64_t)P.n, tile0 = (int64_t)blockIdx.x * DENSE_TILE;
+	const uint64_t readable = P.n_chunks * 16;
+	const uint64_t avail = (readable - (uint64_t)tile0) & ~15ull;
+	const uint32_t loaded = (uint32_t)(avail < (uint64_t)(DENSE_TILE + DENSE_TAIL) ? avail : (uint64_t)(DENSE_TILE + DENSE_TAIL));
+	if (tid == 0) {
+		mbar_init(&s_bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		mbar_expect_tx(&s_bar, loaded);
+		bulk_g2s(s_text, P.text + tile0, loaded, &s_bar);
+	}
+	DevConsts<T> C;
+	shared_init<T, NR>(SH, C, P.desc, DENSE_THREADS);                  /* ends with __syncthreads(): the barrier init is visible */
+	mbar_wait(&s_bar, 0);
+	const int L = C.L;
+	/* bytes [tile0, tile0 + in_smem) come from shared memory: staged AND inside the text */
+	const uint32_t in_smem = (uint32_t)((int64_t)loaded < n - tile0 ? (int64_t)loaded : n - tile0);
+	const uint32_t tile_len = (uint32_t)((int64_t)DENSE_TILE < n - tile0 ? (int64_t)DENSE_TILE : n - tile0);   /* record starts are looked for in [tile0, tile0 + tile_len] */
+	Reader R; R.init(P.text, P.n, SH.delim, L);
+
+	/* ---- 1. record starts in the tile: s = q + 1 for a delimiter ending at q in [tile0 - 1, tile0 + tile_len - 1];
+	 *         s = 0 (tile 0) is the start of the text.  Thread t looks at 128 consecutive q. ---- */
+	const uint32_t per = DENSE_TILE / DENSE_THREADS;
+	uint32_t mine = 0;
+	uint64_t bits[per / 64];
+#pragma unroll
+	for (int w = 0; w < (int)(per / 64); w++) bits[w] = 0;
+	for (uint32_t j = 0; j < per; j++) {
+		const int64_t s_rel = (int64_t)tid * per + j;                  /* candidate start, relative to tile0 */
+		if (s_rel > (int64_t)tile_len || tile0 + s_rel > n) break;
+		bool st;
+		if (tile0 + s_rel == 0) st = true;
+		else {
+			const int64_t q = tile0 + s_rel - 1;
+			if (L == 1) st = (s_rel >= 1 ? s_text[s_rel - 1] : R.get(q)) == SH.delim[0];
+			else st = delim_ends_at(R, q, SH.delim, L, C.kind);
+		}
+		/* a start exactly at tile0 + DENSE_TILE belongs to the next tile */
+		if (st && s_rel < DENSE_TILE) { bits[j >> 6] |= 1ull << (j & 63); mine++; }
+	}
+	s_scan[tid] = mine;
+	__syncthreads();
+	for (int off = 1; off < DENSE_THREADS; off <<= 1) {
+		uint32_t v = (tid >= (unsigned)off) ? s_scan[tid - off] : 0;
+		__syncthreads();
+		s_scan[tid] += v;
+		__syncthreads();
+	}
+	const uint32_t my_first = s_scan[tid] - mine, nrec = s_scan[DENSE_THREADS - 1];
+	__syncthreads();
+
+	/* ---- 2. rounds of at most DENSE_CAP records ---- */
+	uint32_t tile_count = 0;                                           /* reported records of earlier rounds (uniform) */
+	for (uint32_t r0 = 0; r0 < nrec; r0 += DENSE_CAP) {
+		const uint32_t rn = min(nrec - r0, (uint32_t)DENSE_CAP);
+		{   /* this round's starts, in order */
+			uint32_t at = my_first;
+#pragma unroll
+			for (int w = 0; w < (int)(per / 64); w++)
+				for (uint64_t b = bits[w]; b; b &= b - 1) {
+					if (at >= r0 && at < r0 + rn) s_start[at - r0] = (uint16_t)(tid * per + w * 64 + (__ffsll((long long)b) - 1));
+					at++;
+				}
+		}
+		__syncthreads();
+		/* ---- 3. one record per thread at a time ---- */
+		for (uint32_t i = tid; i < rn; i += DENSE_THREADS) {
+			const int64_t s = tile0 + s_start[i];
+			T S[NR];
+			int64_t begin;
+			if (s == 0) {
+#pragma unroll
+				for (int r = 0; r < NR; r++) S[r] = SH.start[r];
+				begin = SH.start_closes ? -(int64_t)L : 0;
+			} else {
+#pragma unroll
+				for (int r = 0; r < NR; r++) S[r] = SH.reset[r];
+				begin = s - L;
+			}
+			int64_t close_at = -1;
+			uint32_t p_rel = s_start[i];
+			bool closed = false;
+			for (; p_rel < in_smem; p_rel++) {                         /* the fast part: bytes from shared memory */
+				rows_step<T, NR, COSTS>(S, SH.mask[s_text[p_rel]], C);
+				if (S[0] & C.dendpos) { close_at = tile0 + p_rel; closed = true; break; }
+			}
+			if (!closed) {                                             /* the record outruns the staged bytes, or the text ends */
+				const int64_t limit = n + L;
+				for (int64_t p = tile0 + p_rel; p < limit; p++) {
+					rows_step<T, NR, COSTS>(S, SH.mask[R.get(p)], C);
+					if (S[0] & C.dendpos) { close_at = p; closed = true; break; }
+				}
+			}
+			int level = -1;
+			if (closed) {
+				const int64_t end = close_at + 1 - L;
+				const bool counts = (begin + 1 < n) && (begin + 1 <= end);       /* bitap.c:213 + agrep.c:3811 */
+				bool cond;
+				int lvl = C.k;
+				if (P.levels) {
+					lvl = -1;
+#pragma unroll
+					for (int r = 0; r < NR; r++) if (lvl < 0 && match_cond<T>(S[r], C)) lvl = r;
+					cond = lvl >= 0;
+					if (cond && counts && !P.emit) atomicAdd(&SH.hist[lvl], 1ull);
+					if (cond && P.want_level >= 0 && lvl > P.want_level) cond = false;
+				} else cond = match_cond<T>(S[NR - 1], C);
+				if (cond && counts) level = lvl;
+				s_close[i] = (unsigned long long)end;
+			}
+			s_level[i] = (int8_t)level;
+		}
+		__syncthreads();
+		/* ---- 4. count, and in the emit pass write this round's reported records in order ---- */
+		uint32_t c8 = 0;
+		for (uint32_t i = tid * 8; i < min(rn, tid * 8 + 8); i++) c8 += s_level[i] >= 0;
+		s_scan[tid] = c8;
+		__syncthreads();
+		for (int off = 1; off < DENSE_THREADS; off <<= 1) {
+			uint32_t v = (tid >= (unsigned)off) ? s_scan[tid - off] : 0;
+			__syncthreads();
+			s_scan[tid] += v;
+			__syncthreads();
+		}
+		if (P.emit) {
+			uint64_t at = P.tile_offsets[blockIdx.x] + tile_count + (s_scan[tid] - c8);
+			for (uint32_t i = tid * 8; i < min(rn, tid * 8 + 8); i++) {
+				if (s_level[i] < 0) continue;
+				if (at < P.capacity) {
+					const int64_t s = tile0 + s_start[i];
+					agb_record rec;
+					rec.begin = (s == 0) ? (SH.start_closes ? -(int64_t)L : 0) : s - L;
+					rec.end = (int64_t)s_close[i]; rec.ordinal = 0; rec.level = s_level[i]; rec.pad = 0;
+					P.records[at] = rec;
+				}
+				at++;
+			}
+		}
+		if (tid == 0) s_total = s_scan[DENSE_THREADS - 1];
+		__syncthreads();
+		tile_count += s_total;
+		__syncthreads();
+	}
+	if (!P.emit && tid == 0) {
+		P.tile_counts[blockIdx.x] = tile_count;
+		if (tile_count) atomicAdd(&P.totals[0], (unsigned long long)tile_count);
+		atomicAdd(&P.totals[1], (unsigned long long)((tile_len + 15) / 16));
+	}
+	if (!P.emit && P.levels && tid <= AGB_MAXERR && SH.hist[tid]) atomicAdd(&P.totals[2 + tid], SH.hist[tid]);
+}
+
 /* list form: one thread per surviving chunk of the ordered candidate list (all lanes busy however sparse the
  * survivors are).  Count launch: per-candidate counts; emit launch: writes at the scanned offsets. */
 template <typename T, int NR, bool COSTS>
@@ -770,7 +945,7 @@ static int ws_prepare(Workspace &W, uint64_t n)
 		int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
 		CUDA_TRY(cudaDeviceGetAttribute(&W.sm_count, cudaDevAttrMultiProcessorCount, dev));
 	}
-	uint64_t n_chunks = (n + 15) / 16, n_words = (n_chunks + 31) / 32, tiles = (n_words + REC_THREADS - 1) / REC_THREADS;
+	uint64_t n_chunks = (n + 15) / 16, n_words = (n_chunks + 31) / 32, tiles = (n + DENSE_TILE - 1) / DENSE_TILE + 1;
 	size_t bb = (size_t)(n_words + FRONT_WORDS_PER_STAGE) * 4;
 	if (bb > W.bitmap_bytes) {
 		if (W.bitmap) cudaFree(W.bitmap);
@@ -914,6 +1089,43 @@ static int launch_records(const agb_desc &d, const RecParams &P, unsigned grid, 
 	return narrow ? launch_records_t<uint32_t, false>(d.nrows, P, grid, st) : launch_records_t<uint64_t, false>(d.nrows, P, grid, st);
 }
 
+#define DENSE_SMEM (DENSE_TILE + DENSE_TAIL)
+template <typename T, int NR, bool COSTS>
+static void launch_dense_one(const RecParams &P, unsigned grid, cudaStream_t st)
+{
+	static bool configured[64] = {false};
+	int dev = 0; cudaGetDevice(&dev);
+	if (!configured[dev & 63]) {
+		cudaFuncSetAttribute(k_records_dense<T, NR, COSTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_SMEM);
+		configured[dev & 63] = true;
+	}
+	k_records_dense<T, NR, COSTS><<<grid, DENSE_THREADS, DENSE_SMEM, st>>>(P);
+}
+template <typename T, bool COSTS>
+static int launch_dense_t(int nrows, const RecParams &P, unsigned grid, cudaStream_t st)
+{
+	switch (nrows) {
+	case 1: launch_dense_one<T, 1, COSTS>(P, grid, st); break;
+	case 2: launch_dense_one<T, 2, COSTS>(P, grid, st); break;
+	case 3: launch_dense_one<T, 3, COSTS>(P, grid, st); break;
+	case 4: launch_dense_one<T, 4, COSTS>(P, grid, st); break;
+	case 5: launch_dense_one<T, 5, COSTS>(P, grid, st); break;
+	case 6: launch_dense_one<T, 6, COSTS>(P, grid, st); break;
+	case 7: launch_dense_one<T, 7, COSTS>(P, grid, st); break;
+	case 8: launch_dense_one<T, 8, COSTS>(P, grid, st); break;
+	case 9: launch_dense_one<T, 9, COSTS>(P, grid, st); break;
+	default: return -1;
+	}
+	g_launches++;
+	return 0;
+}
+static int launch_dense(const agb_desc &d, const RecParams &P, unsigned grid, cudaStream_t st)
+{
+	const bool costs = d.engine == AGB_ENGINE_ASEARCH1, narrow = d.M <= 31;
+	if (costs) return narrow ? launch_dense_t<uint32_t, true>(d.nrows, P, grid, st) : launch_dense_t<uint64_t, true>(d.nrows, P, grid, st);
+	return narrow ? launch_dense_t<uint32_t, false>(d.nrows, P, grid, st) : launch_dense_t<uint64_t, false>(d.nrows, P, grid, st);
+}
+
 template <typename T, bool COSTS>
 static int launch_refine_t(int nrows, const RefineParams &P, unsigned grid, cudaStream_t st)
 {
@@ -1034,6 +1246,19 @@ static int records_launch(const agb_desc &d, Workspace &W, const void *d_text, u
 		CUDA_TRY(cudaMemsetAsync(W.totals + 1, 0, sizeof(unsigned long long), st));
 	}
 	P.tile_counts = W.tile_counts; P.tile_offsets = W.tile_offsets;
+	if (!use_front) {
+		/* no bitmap at all: the dense tile kernel, one CTA per 32 KiB (tile_counts has n/64KiB... entries: 2 per REC tile) */
+		const uint64_t dtiles = (n + DENSE_TILE - 1) / DENSE_TILE;
+		if (launch_dense(d, P, (unsigned)dtiles, st)) return AGB_ERR_ARG;
+		CUDA_TRY(cudaGetLastError());
+		if (want_list) {
+			k_scan_tiles<<<1, 1024, 0, st>>>(W.tile_counts, W.tile_offsets, dtiles, nullptr); g_launches++;
+			P.emit = 1;
+			if (launch_dense(d, P, (unsigned)dtiles, st)) return AGB_ERR_ARG;
+			CUDA_TRY(cudaGetLastError());
+		}
+		return AGB_OK;
+	}
 	if (launch_records(d, P, (unsigned)tiles, st)) return AGB_ERR_ARG;
 	CUDA_TRY(cudaGetLastError());
 	if (want_list) {

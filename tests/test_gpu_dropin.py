@@ -71,3 +71,19 @@ def test_same_stdout_as_reference(files, args, names):
     assert d[2].replace(b"agrep_dropin", b"agrep") == r[2], (d[2], r[2])
     assert d[1] == r[1]
     assert d[0] == r[0]
+
+
+CLI = os.path.join(ROOT, "agrep_b200", "agrep-b200")
+CLI_CASES = [c for c in CASES if not any(a in ("-L2",) or a.startswith("-S") for a in c[0]) and c[0][-1] not in ("a#d;world",)]
+
+
+@pytest.mark.parametrize("args,names", CLI_CASES)
+def test_standalone_cli_prints_what_the_reference_prints(files, args, names):
+    """agrep-b200 (agrep_b200/csrc/agrep_main.c): our own main() + output() restatement over the engine."""
+    if not os.path.exists(CLI):
+        pytest.skip("agrep-b200 not built")
+    fl = [files[n] for n in names]
+    r = run(REF, args + fl)                      # default verbosity: with the "Grand Total" line
+    d = run(CLI, args + fl)
+    assert d[1] == r[1]
+    assert d[0] == r[0]
