@@ -94,7 +94,8 @@ static int scan_files(const agb_pattern *p, char **files, int nfiles, int counti
 		if (cap) recs = (agb_record *)malloc(cap * sizeof *recs);
 		rc = agb_scan_host(p, hb + 1, n, count_only ? AGB_WANT_COUNT : AGB_WANT_RECORDS, recs, cap, &res);
 		if (rc) { fprintf(stderr, "%s: scan failed: %s\n", prog, agb_last_error()); exit(255); }   /* no CPU fallback */
-		if (count_only) num_of_matched += (int)res.n_matched;
+		if (FILENAMEONLY && !counting) num_of_matched += res.n_matched ? 1 : 0;   /* the scan stops at the first hit (bitap.c:184-210, sgrep.c:813-814) */
+		else if (count_only) num_of_matched += (int)res.n_matched;
 		else {
 			ordinals(hb, n, d, recs, (size_t)res.n_records);
 			for (i = 0; i < res.n_records; i++) print_record(hb, d, &recs[i], fname ? fname : "");

@@ -112,8 +112,52 @@ static void fill_ordinals(const unsigned char *hb, size_t n, const unsigned char
 	}
 }
 
+/* The anchor plan (stage 1 / 1.5 of the device scan) from the reference's INTERNAL pattern string, i.e. what
+ * preprocess() hands to maskgen() and bitap() (preproce.c:221-341; symbols agrep.h:69-87): positions are counted
+ * exactly as maskgen() counts them, literal runs are cut into k+1 disjoint anchors of 4 (3, 2) bytes.  Only for a
+ * single pattern part without '#', not under -v or -p -- otherwise every chunk goes to the record stage. */
+enum { S_HYPHEN = 129, S_NOCARE = 130, S_NNLINE = 131, S_WORDB = 133, S_LPAREN = 134, S_RPAREN = 135, S_LRANGE = 136,
+       S_RRANGE = 137, S_LANGLE = 138, S_RANGLE = 139, S_NOT = 140, S_WILD = 141, S_ORSYM = 142, S_ORPAT = 143,
+       S_ANDPAT = 144, S_STAR = 145 };
+
+static void plan_from_internal(const unsigned char *P, int L, int D, agb_desc *d)
+{
+	int lit[80], n = 0, i, seps = 0, A, plen = (int)strlen((const char *)P);
+	d->plan = AGB_PLAN_ALL; d->n_anchors = 0; d->refine = 0;
+	if (INVERSE || I == 0 || wildmask) return;
+	for (i = 0; i < plen && n < 70; i++) {
+		int c = P[i];
+		if (c == S_LANGLE || c == S_RANGLE || c == S_LPAREN || c == S_RPAREN || c == S_STAR || c == S_ORSYM) continue;
+		if (c == S_WILD) return;
+		if (c == S_ORPAT || c == S_ANDPAT) { if (++seps > 1) return; lit[++n] = -1; continue; }
+		if (c == S_LRANGE) { while (i < plen && P[i] != S_RRANGE) i++; lit[++n] = -1; continue; }
+		if (c == '\n' || c >= 128) { lit[++n] = -1; continue; }                 /* newline, WORDB, NNLINE, NOCARE: a position, not a literal */
+		lit[++n] = NOUPPER && c >= 'A' && c <= 'Z' ? c + 32 : c;
+		/* (bytes >= 128 were excluded above: under -i the exact engine folds them through LUT[], bitap.c:171) */
+	}
+	if (n != d->M) return;                                                          /* our count must agree with maskgen's */
+	for (A = 4; A >= 2; A--) {
+		int got = 0, run = 0, p;
+		for (p = L + 2; p <= n && got < D + 1; p++) {
+			if (lit[p] < 0) { run = 0; continue; }
+			if (++run == A) {
+				uint32_t v = 0; int t;
+				for (t = 0; t < A; t++) v |= (uint32_t)lit[p - A + 1 + t] << (8 * t);
+				d->anchor[got] = v; d->anchor_off[got] = p - A + 1 - (L + 2); got++; run = 0;
+			}
+		}
+		if (got < D + 1) continue;
+		d->plan = AGB_PLAN_ANCHORS; d->n_anchors = D + 1; d->anchor_len = A;
+		d->anchor_mask = A == 4 ? 0xFFFFFFFFu : (A == 3 ? 0x00FFFFFFu : 0x0000FFFFu);
+		d->anchor_fold = NOUPPER ? 0x20202020u : 0;
+		for (p = 0; p < d->n_anchors; p++) d->anchor[p] = (d->anchor[p] | d->anchor_fold) & d->anchor_mask;
+		d->pat_len = n - L - 1; d->refine = 1;
+		return;
+	}
+}
+
 /* the common tail of bitap()/asearch*(): desc from the globals, scan, replay through output() */
-static int scan_and_replay(char old_D_pat[], int fd, int M, int D, int engine)
+static int scan_and_replay(char old_D_pat[], const unsigned char *Pattern, int fd, int M, int D, int engine)
 {
 	agb_desc d; agb_pattern *p = NULL; agb_result res; agb_record *recs = NULL;
 	unsigned char dpat[2 * AGB_MAXDELIM + 2], *hb; size_t n = 0, cap, i; int L, c, rc, ret = 0;
@@ -140,6 +184,7 @@ static int scan_and_replay(char old_D_pat[], int fd, int M, int D, int engine)
 	d.k = D; d.engine = engine; d.and_mode = AND; d.inverse = INVERSE; d.user_delim = DELIMITER; d.outtail = OUTTAIL;
 	d.cost_i = I > D ? D + 1 : I; d.cost_s = S > D ? D + 1 : S; d.cost_d = DD > D ? D + 1 : DD;   /* asearch1.c:42-44 */
 	if (d.cost_i < 1) d.cost_i = 1;
+	if (Pattern) plan_from_internal(Pattern, L, D, &d);
 	rc = agb_pattern_from_desc(&d, &p, err, sizeof err);
 	if (rc) { fprintf(stderr, "%s: %s\n", Progname, err); errno = AGREP_ERROR; return -1; }
 
@@ -191,16 +236,15 @@ done:
 
 int bitap(char old_D_pat[], char *Pattern, int fd, int M, int D)
 {
-	(void)Pattern;
 	if (REGEX) {                                            /* bitap.c:96-111: stays with the reference's NFA code */
 		if (D > 4) { fprintf(stderr, "%s: the maximum number of erorrs allowed for full regular expressions is 4\n", Progname); errno = AGREP_ERROR; return -1; }
 		D_length = (int)strlen(old_D_pat);
 		return M <= SHORTREG ? re(fd, M, D) : re1(fd, M, D);
 	}
-	if (D > 0 && JUMP == 1) return scan_and_replay(old_D_pat, fd, M, D, AGB_ENGINE_ASEARCH1);   /* bitap.c:113-116 */
-	if (D > 4) return scan_and_replay(old_D_pat, fd, M, D, AGB_ENGINE_ASEARCH0);               /* asearch.c:50-52 */
-	if (D > 0) return scan_and_replay(old_D_pat, fd, M, D, AGB_ENGINE_ASEARCH);                /* bitap.c:118-121 */
-	return scan_and_replay(old_D_pat, fd, M, D, AGB_ENGINE_BITAP);
+	if (D > 0 && JUMP == 1) return scan_and_replay(old_D_pat, (const unsigned char *)Pattern, fd, M, D, AGB_ENGINE_ASEARCH1);   /* bitap.c:113-116 */
+	if (D > 4) return scan_and_replay(old_D_pat, (const unsigned char *)Pattern, fd, M, D, AGB_ENGINE_ASEARCH0);               /* asearch.c:50-52 */
+	if (D > 0) return scan_and_replay(old_D_pat, (const unsigned char *)Pattern, fd, M, D, AGB_ENGINE_ASEARCH);                /* bitap.c:118-121 */
+	return scan_and_replay(old_D_pat, (const unsigned char *)Pattern, fd, M, D, AGB_ENGINE_BITAP);
 }
 
 /* M is not a parameter of these three in the reference; it is recovered from the always-on bits of Init[0] */
@@ -211,11 +255,11 @@ static int positions_from_init0(void)
 	return M;
 }
 int asearch(unsigned char old_D_pat[], int text, unsigned D)
-{ return scan_and_replay((char *)old_D_pat, text, positions_from_init0(), (int)D, D > 4 ? AGB_ENGINE_ASEARCH0 : AGB_ENGINE_ASEARCH); }
+{ return scan_and_replay((char *)old_D_pat, NULL, text, positions_from_init0(), (int)D, D > 4 ? AGB_ENGINE_ASEARCH0 : AGB_ENGINE_ASEARCH); }
 int asearch0(unsigned char old_D_pat[], int text, unsigned D)
-{ return scan_and_replay((char *)old_D_pat, text, positions_from_init0(), (int)D, AGB_ENGINE_ASEARCH0); }
+{ return scan_and_replay((char *)old_D_pat, NULL, text, positions_from_init0(), (int)D, AGB_ENGINE_ASEARCH0); }
 int asearch1(char old_D_pat[], int Text, unsigned D)
-{ return scan_and_replay(old_D_pat, Text, positions_from_init0(), (int)D, AGB_ENGINE_ASEARCH1); }
+{ return scan_and_replay(old_D_pat, NULL, Text, positions_from_init0(), (int)D, AGB_ENGINE_ASEARCH1); }
 
 /* sgrep(): simple patterns (checksg.c:138).  k = 0: bm() semantics (ASCII case folded literal, once per record,
  * -w by isalnum neighbours, sgrep.c:741-755).  k > 0: the reference runs lossy filters here;

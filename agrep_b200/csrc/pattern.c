@@ -302,12 +302,14 @@ int agbi_derive(agb_desc *d, char *err, size_t errlen)
 
 /* pigeonhole anchor plan: k errors can damage at most k of k+1 disjoint runs of consecutive literal
  * positions, so a matching record contains one run verbatim (the idea of sgrep.c:1053-1154, made exact). */
-static int collect_runs(const build_t *b, int part, int A, uint32_t *out, int *where, int cap)
+static int collect_runs(const build_t *b, int part, int A, int ascii_only, uint32_t *out, int *where, int cap)
 {
 	int p, run = 0, n = 0;
 	for (p = 1; p <= b->n; p++) {
 		const pos_t *q = &b->p[p];
-		if (q->part != part || q->is_sep || q->lit < 0 || q->lit == '\n') { run = 0; continue; }
+		/* ascii_only (-i): the exact engine folds bytes >= 0x80 through the ISO-8859-1 LUT (bitap.c:171), which the
+		 * anchors' plain 0x20 fold cannot express -- such bytes never sit inside an anchor */
+		if (q->part != part || q->is_sep || q->lit < 0 || q->lit == '\n' || (ascii_only && q->lit >= 0x80)) { run = 0; continue; }
 		if (++run == A) {
 			uint32_t v = 0; int t;
 			for (t = 0; t < A; t++) v |= (uint32_t)(b->p[p - A + 1 + t].lit & 0xFF) << (8 * t);
@@ -328,14 +330,14 @@ static void plan_anchors(const build_t *b, agb_desc *d, const agb_options *o, in
 		uint32_t got[AGB_MAXANCHOR]; int pos[AGB_MAXANCHOR], ngot = 0, ok = 1;
 		if (b->or_seen) {                    /* a,b : any alternative may match -> k+1 runs from each */
 			for (part = 1; part <= b->nparts && ok; part++) {
-				uint32_t tmp[AGB_MAXANCHOR]; int tp[AGB_MAXANCHOR], nt = collect_runs(b, part, A, tmp, tp, AGB_MAXANCHOR);
+				uint32_t tmp[AGB_MAXANCHOR]; int tp[AGB_MAXANCHOR], nt = collect_runs(b, part, A, o->nocase || fold_all, tmp, tp, AGB_MAXANCHOR);
 				if (nt < d->k + 1 || ngot + d->k + 1 > AGB_MAXANCHOR) ok = 0;
 				else { memcpy(got + ngot, tmp, sizeof(uint32_t) * (size_t)(d->k + 1)); memcpy(pos + ngot, tp, sizeof(int) * (size_t)(d->k + 1)); ngot += d->k + 1; }
 			}
 		} else {                             /* single pattern or a;b (all must match): the part richest in runs */
 			int best = -1;
 			for (part = 1; part <= b->nparts; part++) {
-				uint32_t tmp[AGB_MAXANCHOR]; int tp[AGB_MAXANCHOR], nt = collect_runs(b, part, A, tmp, tp, AGB_MAXANCHOR);
+				uint32_t tmp[AGB_MAXANCHOR]; int tp[AGB_MAXANCHOR], nt = collect_runs(b, part, A, o->nocase || fold_all, tmp, tp, AGB_MAXANCHOR);
 				if (nt > best) { best = nt; memcpy(got, tmp, sizeof(uint32_t) * (size_t)nt); memcpy(pos, tp, sizeof(int) * (size_t)nt); }
 			}
 			if (best < d->k + 1) ok = 0; else ngot = d->k + 1;
@@ -500,7 +502,10 @@ int agb_pattern_from_desc(const agb_desc *d, agb_pattern **out, char *err, size_
 	p = (agb_pattern *)calloc(1, sizeof *p);
 	if (!p) return AGB_ERR_NOMEM;
 	p->d = *d;
-	p->d.plan = AGB_PLAN_ALL; p->d.n_anchors = 0;
+	/* the caller may bring its own anchor plan (the drop-in layer derives one from the reference's internal pattern) */
+	if (p->d.plan != AGB_PLAN_ANCHORS || p->d.n_anchors < 1 || p->d.n_anchors > AGB_MAXANCHOR || p->d.anchor_len < 2 || p->d.anchor_len > 4) {
+		p->d.plan = AGB_PLAN_ALL; p->d.n_anchors = 0; p->d.refine = 0;
+	}
 	rc = agbi_derive(&p->d, err, errlen);
 	if (rc) { free(p); *out = NULL; return rc; }
 	*out = p;

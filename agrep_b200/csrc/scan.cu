@@ -567,16 +567,17 @@ k_records(const RecParams P)
 }
 
 /* dense tile form: the automaton over EVERYTHING (no anchor plan: classes, -v, -p, '#', short patterns ...).
- * One CTA per 32 KiB tile.  The tile (+2 KiB that follow it) is brought into shared memory by one bulk-async
- * copy; the threads find the record starts that lie in the tile (a delimiter ends just before them), the block
- * orders them into a list, and every thread takes whole records from that list -- start state = the constant
- * post-delimiter rows, text bytes from shared memory (global memory only for the rare record that outruns the
- * staged bytes), exactly the loop of asearch.c:94-199 until the record closes.  A record belongs to the tile it
- * starts in, so nothing is carried between tiles and the per-tile counts scan into an ordered global list. */
+ * One CTA per 32 KiB tile, brought into shared memory (+2 KiB that follow it) by one bulk-async copy.  Thread t
+ * owns the records whose opening delimiter ends inside its 128-byte slice: it starts at the first of them in the
+ * constant post-delimiter state and simply keeps walking -- a record that closes at a delimiter inside the slice
+ * hands over to the next one at the following byte -- until the last of its records has closed (on average half a
+ * record past the slice; the neighbour skips that head).  So every lane walks about the same number of bytes in
+ * lockstep, bytes and the Mask[] table come from shared memory (global memory only for a record that outruns the
+ * staged bytes), and nothing is carried between threads or tiles.  Same loop as asearch.c:94-199. */
 #define DENSE_THREADS 256
 #define DENSE_TILE    32768
 #define DENSE_TAIL    2048
-#define DENSE_CAP     2048          /* record starts per round */
+#define DENSE_PER     (DENSE_TILE / DENSE_THREADS)          /* 128 bytes per thread */
 
 template <typename T, int NR, bool COSTS>
 __global__ void __launch_bounds__(DENSE_THREADS)
@@ -585,11 +586,7 @@ k_records_dense(const RecParams P)
 	extern __shared__ __align__(128) uint8_t s_text[];                 /* DENSE_TILE + DENSE_TAIL */
 	__shared__ RecShared<T, NR> SH;
 	__shared__ uint64_t s_bar;
-	__shared__ uint16_t s_start[DENSE_CAP];
-	__shared__ unsigned long long s_close[DENSE_CAP];
-	__shared__ int8_t s_level[DENSE_CAP];                              /* -1: not reported */
 	__shared__ uint32_t s_scan[DENSE_THREADS];
-	__shared__ uint32_t s_total;
 	const uint32_t tid = threadIdx.x;
 	const int64_t n = (int64_t)P.n, tile0 = (int64_t)blockIdx.x * DENSE_TILE;
 	const uint64_t readable = P.n_chunks * 16;
@@ -607,138 +604,167 @@ k_records_dense(const RecParams P)
 	const int L = C.L;
 	/* bytes [tile0, tile0 + in_smem) come from shared memory: staged AND inside the text */
 	const uint32_t in_smem = (uint32_t)((int64_t)loaded < n - tile0 ? (int64_t)loaded : n - tile0);
-	const uint32_t tile_len = (uint32_t)((int64_t)DENSE_TILE < n - tile0 ? (int64_t)DENSE_TILE : n - tile0);   /* record starts are looked for in [tile0, tile0 + tile_len] */
+	const uint32_t tile_len = (uint32_t)((int64_t)DENSE_TILE < n - tile0 ? (int64_t)DENSE_TILE : n - tile0);
 	Reader R; R.init(P.text, P.n, SH.delim, L);
 
-	/* ---- 1. record starts in the tile: s = q + 1 for a delimiter ending at q in [tile0 - 1, tile0 + tile_len - 1];
-	 *         s = 0 (tile 0) is the start of the text.  Thread t looks at 128 consecutive q. ---- */
-	const uint32_t per = DENSE_TILE / DENSE_THREADS;
-	uint32_t mine = 0;
-	uint64_t bits[per / 64];
+	/* ---- which delimiters end in my slice (bit j: at byte 128 t + j)?  The record that follows each is mine. ---- */
+	uint64_t bits[DENSE_PER / 64];
 #pragma unroll
-	for (int w = 0; w < (int)(per / 64); w++) bits[w] = 0;
-	for (uint32_t j = 0; j < per; j++) {
-		const int64_t s_rel = (int64_t)tid * per + j;                  /* candidate start, relative to tile0 */
-		if (s_rel > (int64_t)tile_len || tile0 + s_rel > n) break;
-		bool st;
-		if (tile0 + s_rel == 0) st = true;
-		else {
-			const int64_t q = tile0 + s_rel - 1;
-			if (L == 1) st = (s_rel >= 1 ? s_text[s_rel - 1] : R.get(q)) == SH.delim[0];
-			else st = delim_ends_at(R, q, SH.delim, L, C.kind);
+	for (int w = 0; w < DENSE_PER / 64; w++) bits[w] = 0;
+	if (L == 1) {
+		/* 16 bytes at a time: exact per-byte equality by SWAR, 4 flags gathered by one multiply */
+		const uint32_t d4 = SH.delim[0] * 0x01010101u;
+#pragma unroll
+		for (int v = 0; v < DENSE_PER / 16; v++) {
+			const uint4 x = *reinterpret_cast<const uint4 *>(s_text + tid * DENSE_PER + v * 16);
+			const uint32_t xs[4] = { x.x, x.y, x.z, x.w };
+			uint32_t m16 = 0;
+#pragma unroll
+			for (int w = 0; w < 4; w++) {
+				const uint32_t t = xs[w] ^ d4;
+				const uint32_t z = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t | 0x7F7F7F7Fu);    /* 0x80 where the byte equals the delimiter */
+				m16 |= ((((z >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * w);
+			}
+			bits[v >> 2] |= (uint64_t)m16 << (16 * (v & 3));
 		}
-		/* a start exactly at tile0 + DENSE_TILE belongs to the next tile */
-		if (st && s_rel < DENSE_TILE) { bits[j >> 6] |= 1ull << (j & 63); mine++; }
+	} else {
+		for (uint32_t j = 0; j < DENSE_PER; j++) {
+			const int64_t q = tile0 + (int64_t)tid * DENSE_PER + j;
+			if (q < n && delim_ends_at(R, q, SH.delim, L, C.kind)) bits[j >> 6] |= 1ull << (j & 63);
+		}
 	}
-	s_scan[tid] = mine;
-	__syncthreads();
-	for (int off = 1; off < DENSE_THREADS; off <<= 1) {
-		uint32_t v = (tid >= (unsigned)off) ? s_scan[tid - off] : 0;
-		__syncthreads();
-		s_scan[tid] += v;
-		__syncthreads();
+	{   /* only delimiters inside the text (q < n) */
+		const int64_t last_q = (int64_t)tile_len - 1 - (int64_t)tid * DENSE_PER;
+#pragma unroll
+		for (int w = 0; w < DENSE_PER / 64; w++) {
+			const int64_t hi = last_q - 64 * w;
+			if (hi < 0) bits[w] = 0; else if (hi < 63) bits[w] &= (2ull << hi) - 1;
+		}
 	}
-	const uint32_t my_first = s_scan[tid] - mine, nrec = s_scan[DENSE_THREADS - 1];
-	__syncthreads();
+	/* the very first record of the text has no delimiter in front of it: thread 0 of tile 0 */
+	const bool first = (tile0 == 0 && tid == 0);
+	uint32_t owned = first ? 1u : 0u;
+#pragma unroll
+	for (int w = 0; w < DENSE_PER / 64; w++) owned += __popcll(bits[w]);
 
-	/* ---- 2. rounds of at most DENSE_CAP records ---- */
-	uint32_t tile_count = 0;                                           /* reported records of earlier rounds (uniform) */
-	for (uint32_t r0 = 0; r0 < nrec; r0 += DENSE_CAP) {
-		const uint32_t rn = min(nrec - r0, (uint32_t)DENSE_CAP);
-		{   /* this round's starts, in order */
-			uint32_t at = my_first;
+	const int64_t limit = n + L;
+	/* rows after a delimiter, kept in registers: a close is a handful of moves, not shared-memory traffic */
+	T RS[NR];
 #pragma unroll
-			for (int w = 0; w < (int)(per / 64); w++)
-				for (uint64_t b = bits[w]; b; b &= b - 1) {
-					if (at >= r0 && at < r0 + rn) s_start[at - r0] = (uint16_t)(tid * per + w * 64 + (__ffsll((long long)b) - 1));
-					at++;
-				}
-		}
-		__syncthreads();
-		/* ---- 3. one record per thread at a time ---- */
-		for (uint32_t i = tid; i < rn; i += DENSE_THREADS) {
-			const int64_t s = tile0 + s_start[i];
+	for (int r = 0; r < NR; r++) RS[r] = SH.reset[r];
+	/* away from the end of the text every record counts unless it is empty (bitap.c:213, agrep.c:3811) */
+	const bool easy = tile0 + (int64_t)DENSE_TILE + DENSE_TAIL + L + 2 < n;
+	uint32_t my_count = 0;
+	uint64_t out_pos = 0;
+	for (int pass = 0; pass < (P.emit ? 2 : 1); pass++) {
+		uint32_t cnt = 0, left = owned;
+		if (left) {
+			uint32_t rel;                                               /* position relative to tile0 while inside the staged bytes */
+			if (first) rel = 0;
+			else rel = tid * DENSE_PER + 1 + (bits[0] ? __ffsll((long long)bits[0]) - 1 : 64 + __ffsll((long long)bits[1]) - 1);
 			T S[NR];
 			int64_t begin;
-			if (s == 0) {
+			if (tile0 == 0 && rel == 0) {
 #pragma unroll
 				for (int r = 0; r < NR; r++) S[r] = SH.start[r];
 				begin = SH.start_closes ? -(int64_t)L : 0;
 			} else {
 #pragma unroll
-				for (int r = 0; r < NR; r++) S[r] = SH.reset[r];
-				begin = s - L;
+				for (int r = 0; r < NR; r++) S[r] = RS[r];
+				begin = tile0 + rel - L;
 			}
-			int64_t close_at = -1;
-			uint32_t p_rel = s_start[i];
-			bool closed = false;
-			for (; p_rel < in_smem; p_rel++) {                         /* the fast part: bytes from shared memory */
-				rows_step<T, NR, COSTS>(S, SH.mask[s_text[p_rel]], C);
-				if (S[0] & C.dendpos) { close_at = tile0 + p_rel; closed = true; break; }
-			}
-			if (!closed) {                                             /* the record outruns the staged bytes, or the text ends */
-				const int64_t limit = n + L;
-				for (int64_t p = tile0 + p_rel; p < limit; p++) {
-					rows_step<T, NR, COSTS>(S, SH.mask[R.get(p)], C);
-					if (S[0] & C.dendpos) { close_at = p; closed = true; break; }
-				}
-			}
-			int level = -1;
-			if (closed) {
-				const int64_t end = close_at + 1 - L;
-				const bool counts = (begin + 1 < n) && (begin + 1 <= end);       /* bitap.c:213 + agrep.c:3811 */
-				bool cond;
-				int lvl = C.k;
-				if (P.levels) {
-					lvl = -1;
+			uint32_t begin_rel = (uint32_t)(begin - tile0);              /* begin - tile0 (mod 2^32; -1 for the virtual newline) */
+			/* ---- fast part: text bytes from shared memory, 32-bit bookkeeping ---- */
+			for (; rel < in_smem; rel++) {
+				rows_step<T, NR, COSTS>(S, SH.mask[s_text[rel]], C);
+				if (S[0] & C.dendpos) {
+					const uint32_t end_rel = rel + 1 - L;
+					bool counts = (int32_t)(end_rel - begin_rel) >= 1;  /* begin + 1 <= end (agrep.c:3811) */
+					if (!easy) counts = counts && (tile0 + (int64_t)(int32_t)begin_rel + 1 < n);
+					int level = C.k;
+					bool cond;
+					if (P.levels) {
+						level = -1;
 #pragma unroll
-					for (int r = 0; r < NR; r++) if (lvl < 0 && match_cond<T>(S[r], C)) lvl = r;
-					cond = lvl >= 0;
-					if (cond && counts && !P.emit) atomicAdd(&SH.hist[lvl], 1ull);
-					if (cond && P.want_level >= 0 && lvl > P.want_level) cond = false;
-				} else cond = match_cond<T>(S[NR - 1], C);
-				if (cond && counts) level = lvl;
-				s_close[i] = (unsigned long long)end;
-			}
-			s_level[i] = (int8_t)level;
-		}
-		__syncthreads();
-		/* ---- 4. count, and in the emit pass write this round's reported records in order ---- */
-		uint32_t c8 = 0;
-		for (uint32_t i = tid * 8; i < min(rn, tid * 8 + 8); i++) c8 += s_level[i] >= 0;
-		s_scan[tid] = c8;
-		__syncthreads();
-		for (int off = 1; off < DENSE_THREADS; off <<= 1) {
-			uint32_t v = (tid >= (unsigned)off) ? s_scan[tid - off] : 0;
-			__syncthreads();
-			s_scan[tid] += v;
-			__syncthreads();
-		}
-		if (P.emit) {
-			uint64_t at = P.tile_offsets[blockIdx.x] + tile_count + (s_scan[tid] - c8);
-			for (uint32_t i = tid * 8; i < min(rn, tid * 8 + 8); i++) {
-				if (s_level[i] < 0) continue;
-				if (at < P.capacity) {
-					const int64_t s = tile0 + s_start[i];
-					agb_record rec;
-					rec.begin = (s == 0) ? (SH.start_closes ? -(int64_t)L : 0) : s - L;
-					rec.end = (int64_t)s_close[i]; rec.ordinal = 0; rec.level = s_level[i]; rec.pad = 0;
-					P.records[at] = rec;
+						for (int r = 0; r < NR; r++) if (level < 0 && match_cond<T>(S[r], C)) level = r;
+						cond = level >= 0;
+						if (cond && counts && pass == 0 && !P.emit) atomicAdd(&SH.hist[level], 1ull);
+						if (cond && P.want_level >= 0 && level > P.want_level) cond = false;
+					} else cond = match_cond<T>(S[NR - 1], C);
+					if (cond && counts) {
+						if (pass == 1) {
+							const uint64_t at = out_pos + cnt;
+							if (at < P.capacity) {
+								agb_record rec; rec.begin = tile0 + (int64_t)(int32_t)begin_rel; rec.end = tile0 + end_rel;
+								rec.ordinal = 0; rec.level = level; rec.pad = 0;
+								P.records[at] = rec;
+							}
+						}
+						cnt++;
+					}
+					if (--left == 0) break;                               /* the record that starts at the next byte is somebody else's */
+#pragma unroll
+					for (int r = 0; r < NR; r++) S[r] = RS[r];
+					begin_rel = end_rel;
 				}
-				at++;
+			}
+			/* ---- slow part: the record outruns the staged bytes or the text ends (appended delimiter) ---- */
+			if (left) {
+				begin = tile0 + (int64_t)(int32_t)begin_rel;
+				for (int64_t p = tile0 + rel; p < limit; p++) {
+					rows_step<T, NR, COSTS>(S, SH.mask[R.get(p)], C);
+					if (S[0] & C.dendpos) {
+						const int64_t end = p + 1 - L;
+						const bool counts = (begin + 1 < n) && (begin + 1 <= end);
+						int level = C.k;
+						bool cond;
+						if (P.levels) {
+							level = -1;
+#pragma unroll
+							for (int r = 0; r < NR; r++) if (level < 0 && match_cond<T>(S[r], C)) level = r;
+							cond = level >= 0;
+							if (cond && counts && pass == 0 && !P.emit) atomicAdd(&SH.hist[level], 1ull);
+							if (cond && P.want_level >= 0 && level > P.want_level) cond = false;
+						} else cond = match_cond<T>(S[NR - 1], C);
+						if (cond && counts) {
+							if (pass == 1) {
+								const uint64_t at = out_pos + cnt;
+								if (at < P.capacity) {
+									agb_record rec; rec.begin = begin; rec.end = end; rec.ordinal = 0; rec.level = level; rec.pad = 0;
+									P.records[at] = rec;
+								}
+							}
+							cnt++;
+						}
+						if (--left == 0) break;
+#pragma unroll
+						for (int r = 0; r < NR; r++) S[r] = RS[r];
+						begin = end;
+					}
+				}
 			}
 		}
-		if (tid == 0) s_total = s_scan[DENSE_THREADS - 1];
-		__syncthreads();
-		tile_count += s_total;
-		__syncthreads();
+		if (pass == 0) {
+			my_count = cnt;
+			s_scan[tid] = cnt;
+			__syncthreads();
+			for (int off = 1; off < DENSE_THREADS; off <<= 1) {
+				uint32_t v = (tid >= (unsigned)off) ? s_scan[tid - off] : 0;
+				__syncthreads();
+				s_scan[tid] += v;
+				__syncthreads();
+			}
+			if (!P.emit) {
+				if (tid == DENSE_THREADS - 1) {
+					P.tile_counts[blockIdx.x] = s_scan[DENSE_THREADS - 1];
+					if (s_scan[DENSE_THREADS - 1]) atomicAdd(&P.totals[0], (unsigned long long)s_scan[DENSE_THREADS - 1]);
+					atomicAdd(&P.totals[1], (unsigned long long)((tile_len + 15) / 16));
+				}
+				__syncthreads();
+				if (P.levels && tid <= AGB_MAXERR && SH.hist[tid]) atomicAdd(&P.totals[2 + tid], SH.hist[tid]);
+			} else out_pos = P.tile_offsets[blockIdx.x] + (s_scan[tid] - my_count);
+		}
 	}
-	if (!P.emit && tid == 0) {
-		P.tile_counts[blockIdx.x] = tile_count;
-		if (tile_count) atomicAdd(&P.totals[0], (unsigned long long)tile_count);
-		atomicAdd(&P.totals[1], (unsigned long long)((tile_len + 15) / 16));
-	}
-	if (!P.emit && P.levels && tid <= AGB_MAXERR && SH.hist[tid]) atomicAdd(&P.totals[2 + tid], SH.hist[tid]);
 }
 
 /* list form: one thread per surviving chunk of the ordered candidate list (all lanes busy however sparse the
@@ -960,8 +986,15 @@ static int ws_prepare(Workspace &W, uint64_t n)
 		CUDA_TRY(cudaMalloc(&W.tile_offsets, (tiles + 1) * sizeof(uint64_t)));
 		W.tiles = tiles + 1;
 	}
-	size_t want_cand = std::max<size_t>((size_t)1 << 20, (size_t)(n_chunks / 128));
+	return AGB_OK;
+}
+
+/* the candidate list of the list form is sized by what stage 1.5 actually left (known on the host by then) */
+static int ws_cand_reserve(Workspace &W, size_t want_cand)
+{
+	want_cand = std::max<size_t>(want_cand, (size_t)1 << 20);
 	if (want_cand > W.cand_cap) {
+		want_cand += want_cand / 4;
 		if (W.cand) cudaFree(W.cand);
 		if (W.cand_counts) cudaFree(W.cand_counts);
 		if (W.cand_offsets) cudaFree(W.cand_offsets);
@@ -1219,15 +1252,15 @@ static int records_launch(const agb_desc &d, Workspace &W, const void *d_text, u
 	P.totals = W.totals; P.emit = 0; P.levels = (want & AGB_WANT_LEVELS) ? 1 : 0; P.want_level = want_level;
 	if (!tiles) return AGB_OK;
 	const bool want_list = (want & AGB_WANT_RECORDS) && capacity;
-	RefineParams geo; memset(&geo, 0, sizeof geo);
-	if (use_front && refine_geometry(d, geo)) {
+	if (use_front) {
 		const uint64_t blocks = (n_words + COMPACT_THREADS * COMPACT_WPT - 1) / (COMPACT_THREADS * COMPACT_WPT);
 		k_compact_count<<<(unsigned)blocks, COMPACT_THREADS, 0, st>>>(W.bitmap, n_words, W.tile_counts, W.totals); g_launches++;
 		k_scan_tiles<<<1, 1024, 0, st>>>(W.tile_counts, W.tile_offsets, blocks, W.totals + 12); g_launches++;
 		CUDA_TRY(cudaMemcpyAsync(W.h_totals + 12, W.totals + 12, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 		CUDA_TRY(cudaStreamSynchronize(st));
 		const unsigned long long ncand = W.h_totals[12];
-		if (ncand <= W.cand_cap) {
+		/* list form while at most a quarter of the chunks survived (20 B of scratch per survivor) */
+		if (ncand <= n_chunks / 4 + 1024 && ws_cand_reserve(W, (size_t)ncand) == AGB_OK) {
 			if (ncand == 0) return AGB_OK;
 			k_compact_write<<<(unsigned)blocks, COMPACT_THREADS, 0, st>>>(W.bitmap, n_words, W.tile_offsets, W.cand, W.cand_cap); g_launches++;
 			P.cand = W.cand; P.cand_cap = W.cand_cap; P.tile_counts = W.cand_counts; P.tile_offsets = W.cand_offsets;
@@ -1242,7 +1275,7 @@ static int records_launch(const agb_desc &d, Workspace &W, const void *d_text, u
 			}
 			return AGB_OK;
 		}
-		/* too many survivors for the list: dense form below (totals[1] is recounted there) */
+		/* too many survivors for a list: bitmap form below (totals[1] is recounted there) */
 		CUDA_TRY(cudaMemsetAsync(W.totals + 1, 0, sizeof(unsigned long long), st));
 	}
 	P.tile_counts = W.tile_counts; P.tile_offsets = W.tile_offsets;

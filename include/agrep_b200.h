@@ -120,7 +120,8 @@ typedef struct agb_result {
 int  agb_compile(const char *pattern, const agb_options *opt, agb_pattern **out, char *err, size_t errlen);
 void agb_pattern_free(agb_pattern *p);
 const agb_desc *agb_pattern_desc(const agb_pattern *p);
-/* wrap words produced elsewhere (the drop-in layer passes the reference's globals); plan = AGB_PLAN_ALL */
+/* wrap words produced elsewhere (the drop-in layer passes the reference's globals); the plan fields are honoured
+ * when plan == AGB_PLAN_ANCHORS, else every chunk goes to the record stage */
 int  agb_pattern_from_desc(const agb_desc *d, agb_pattern **out, char *err, size_t errlen);
 
 /* ---- device scan ----

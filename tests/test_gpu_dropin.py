@@ -74,7 +74,7 @@ def test_same_stdout_as_reference(files, args, names):
 
 
 CLI = os.path.join(ROOT, "agrep_b200", "agrep-b200")
-CLI_CASES = [c for c in CASES if not any(a in ("-L2",) or a.startswith("-S") for a in c[0]) and c[0][-1] not in ("a#d;world",)]
+CLI_CASES = [c for c in CASES if not any(a in ("-L2", "-s") or a.startswith("-S") for a in c[0]) and c[0][-1] not in ("a#d;world",)]
 
 
 @pytest.mark.parametrize("args,names", CLI_CASES)

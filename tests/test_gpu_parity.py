@@ -146,3 +146,14 @@ def test_bestmatch_sweep():
             assert best == -1
         else:
             assert (best, res.n_matched) == want
+
+
+def test_latin1_case_folding_of_the_exact_engine():
+    """-i with k=0 goes through LUT[] = CP[ISO-8859-1].lower_1 (bitap.c:171): 'É' (0xC9) matches 'é' (0xE9);
+    with k>0 asearch() applies no LUT (asearch.c:96), so it does not."""
+    body = (b"xx caf\xe9 noir yy\nxx CAF\xc9 NOIR yy\nxx cafe noir\nzz \x80\x87 qq caf\xc9\n" * 50) + TEXT[:20000]
+    for kw in (dict(k=0, linenum=1, nocase=1), dict(k=1, linenum=1, nocase=1), dict(k=0, linenum=1), dict(k=0, nocase=1)):
+        check(b"caf\xe9 noir", body, **kw)
+        check(b"\xf6l qq", body.replace(b"cafe noir", b"\xd6L QQ \xf6l qq"), **kw)
+    res = check(b"caf\xe9 noir", body, k=0, linenum=1, nocase=1)
+    assert res.n_matched == 100
