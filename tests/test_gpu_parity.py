@@ -157,3 +157,56 @@ def test_latin1_case_folding_of_the_exact_engine():
         check(b"\xf6l qq", body.replace(b"cafe noir", b"\xd6L QQ \xf6l qq"), **kw)
     res = check(b"caf\xe9 noir", body, k=0, linenum=1, nocase=1)
     assert res.n_matched == 100
+
+
+def test_host_entry_points_agree(tmp_path):
+    """agb_scan_host on pageable and on page-locked memory, and agb_scan_fd on a regular file and on a pipe
+    (the fill_buf replacement, bitap.c:450-477), all give the device-resident answer -- across several 64 MiB slices."""
+    import ctypes, os, torch
+    from agrep_b200 import _lib
+    L = _lib.lib()
+    n = (160 << 20) + 12345                      # 3 slices, ragged tail
+    host = ag.corpus_host((n + 4095) // 4096 * 4096, needle="because each", needle_every=512, needle_maxedits=3)[:n]
+    p = ag.Pattern("because each", k=2)
+    dev = torch.frombuffer(bytearray(host + b"\0" * 64), dtype=torch.uint8).cuda()
+    cap = 1 << 16
+    drec = torch.zeros((cap, 4), dtype=torch.int64, device="cuda")
+    ref = p.scan_device(dev.data_ptr(), n, d_records=drec.data_ptr(), capacity=cap)
+    want = drec[:ref.n_records, :2].cpu().tolist()
+    assert ref.n_matched > 100
+
+    def via(fn):
+        recs = (_lib.Record * cap)()
+        res = _lib.Result()
+        rc = fn(recs, res)
+        assert rc == 0, L.agb_last_error()
+        assert res.n_matched == ref.n_matched
+        assert [[recs[i].begin, recs[i].end] for i in range(res.n_records)] == want
+
+    buf = ctypes.create_string_buffer(host, n)
+    via(lambda recs, res: L.agb_scan_host(p._h, buf, n, _lib.WANT_RECORDS, recs, cap, ctypes.byref(res)))          # pageable
+    pinned = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    pinned.copy_(torch.frombuffer(bytearray(host), dtype=torch.uint8))
+    via(lambda recs, res: L.agb_scan_host(p._h, ctypes.c_void_p(pinned.data_ptr()), n, _lib.WANT_RECORDS, recs, cap, ctypes.byref(res)))
+    path = tmp_path / "corpus.txt"
+    path.write_bytes(host)
+    fd = os.open(str(path), os.O_RDONLY)
+    try:
+        via(lambda recs, res: L.agb_scan_fd(p._h, fd, _lib.WANT_RECORDS, recs, cap, ctypes.byref(res)))               # regular file
+    finally:
+        os.close(fd)
+    r, w = os.pipe()
+    small = host[:3 << 20]
+    pid = os.fork()
+    if pid == 0:
+        os.close(r)
+        os.write(w, small) if False else [os.write(w, small[i:i + 65536]) for i in range(0, len(small), 65536)]
+        os._exit(0)
+    os.close(w)
+    recs = (_lib.Record * cap)()
+    res = _lib.Result()
+    assert L.agb_scan_fd(p._h, r, _lib.WANT_RECORDS, recs, cap, ctypes.byref(res)) == 0                               # pipe
+    os.close(r); os.waitpid(pid, 0)
+    a = _oracle.compile("because each", k=2, linenum=1)
+    cnt, orecs = _oracle.scan(a, small)
+    assert res.n_matched == cnt and [(recs[i].begin, recs[i].end) for i in range(res.n_records)] == [(b, e) for b, e, _ in orecs]
