@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libagrepb200.so")
 
 AGB_MAXERR, AGB_MAXDELIM, AGB_MAXANCHOR = 8, 8, 24
-WANT_COUNT, WANT_RECORDS, WANT_ORDINALS, WANT_LEVELS = 0, 1, 2, 4
+WANT_COUNT, WANT_RECORDS, WANT_LEVELS = 0, 1, 4
 PLAN_ALL, PLAN_ANCHORS = 0, 1
 ENGINE_NAMES = {0: "bitap", 1: "asearch", 2: "asearch0", 3: "asearch1", 4: "sgrep_bm"}
 
@@ -50,7 +50,7 @@ class CorpusSpec(C.Structure):
                 ("needle_maxedits", C.c_int32), ("pad", C.c_int32)]
 
 
-EXPORTS = ["agb_compile", "agb_pattern_free", "agb_pattern_desc", "agb_pattern_from_desc", "agb_scan_device",
+EXPORTS = ["agb_fill_ordinals", "agb_compile", "agb_pattern_free", "agb_pattern_desc", "agb_pattern_from_desc", "agb_scan_device",
            "agb_scan_host", "agb_scan_fd", "agb_bestmatch_device", "agb_corpus_fill_device", "agb_corpus_fill_host",
            "agb_last_error", "agb_device_count", "agb_set_device", "agb_version", "agb_kernel_launches"]
 
@@ -80,6 +80,8 @@ def lib():
                                        C.POINTER(C.c_int), C.POINTER(Result), C.c_char_p, C.c_size_t]
     L.agb_corpus_fill_device.argtypes = [C.POINTER(CorpusSpec), C.c_void_p, C.c_void_p]
     L.agb_corpus_fill_host.argtypes = [C.POINTER(CorpusSpec), C.c_void_p]
+    L.agb_fill_ordinals.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    L.agb_fill_ordinals.restype = None
     L.agb_last_error.restype = C.c_char_p
     L.agb_version.restype = C.c_char_p
     L.agb_kernel_launches.restype = C.c_uint64

@@ -46,22 +46,6 @@ static unsigned char *slurp(const char *path, size_t *n, int L, const unsigned c
 	return b;
 }
 
-/* j for every reported record: closes so far (bitap.c:178), host walk over the delimiters */
-static void ordinals(const unsigned char *hb, size_t n, const agb_desc *d, agb_record *r, size_t nr)
-{
-	size_t q, i = 0; long long j = 0, run = 0; int L = d->L;
-	if (d->user_delim && n >= (size_t)L && memcmp(hb + 1, d->delim, (size_t)L) == 0) j = -1;   /* bitap.c:151-156 */
-	for (q = 0; q <= n + (size_t)L && i < nr; q++) {
-		int e;
-		if (L == 1) e = hb[q] == d->delim[0];
-		else if (d->delim_kind == 0) e = q + 1 >= (size_t)L && memcmp(hb + q + 1 - L, d->delim, (size_t)L) == 0;
-		else { run = hb[q] == d->delim[0] ? run + 1 : 0; e = run > 0 && run % L == 0; }
-		if (!e) continue;
-		j++;
-		while (i < nr && r[i].end + L == (long long)q) r[i++].ordinal = j;
-	}
-}
-
 /* output() of the reference, agrep.c:3805-3956, for the switches we carry */
 static void print_record(const unsigned char *hb, const agb_desc *d, const agb_record *rec, const char *fname)
 {
@@ -97,7 +81,7 @@ static int scan_files(const agb_pattern *p, char **files, int nfiles, int counti
 		if (FILENAMEONLY && !counting) num_of_matched += res.n_matched ? 1 : 0;   /* the scan stops at the first hit (bitap.c:184-210, sgrep.c:813-814) */
 		else if (count_only) num_of_matched += (int)res.n_matched;
 		else {
-			ordinals(hb, n, d, recs, (size_t)res.n_records);
+			agb_fill_ordinals(p, hb + 1, n, recs, res.n_records);
 			for (i = 0; i < res.n_records; i++) print_record(hb, d, &recs[i], fname ? fname : "");
 		}
 		if (!counting) {

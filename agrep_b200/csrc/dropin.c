@@ -92,26 +92,6 @@ static int fail(const char *what)
 	return -1;
 }
 
-/* j of every matching record = number of record closes up to and including its own (bitap.c:178), counted on
- * the host copy only when -n asks for it */
-static void fill_ordinals(const unsigned char *hb, size_t n, const unsigned char *dpat, int L, int kind,
-                          agb_record *recs, size_t nrec, int first_j)
-{
-	size_t r = 0, q; long long j = first_j;
-	/* closes happen at delimiter ends in hb[0 .. n+L]; walk them in order (same greedy rule as the device) */
-	long long run = 0;
-	for (q = 0; q <= n + (size_t)L && r < nrec; q++) {
-		int is_end;
-		if (L == 1) is_end = hb[q] == dpat[0];
-		else if (kind == 0) is_end = q + 1 >= (size_t)L && memcmp(hb + q + 1 - L, dpat, (size_t)L) == 0;
-		else { run = (hb[q] == dpat[0]) ? run + 1 : 0; is_end = run > 0 && (run % L) == 0; }
-		if (!is_end) continue;
-		j++;
-		/* record closing here has end (file offset) = q - L  (buffer index q = file offset q-1) */
-		while (r < nrec && recs[r].end + L == (long long)q) { recs[r].ordinal = j; r++; }
-	}
-}
-
 /* The anchor plan (stage 1 / 1.5 of the device scan) from the reference's INTERNAL pattern string, i.e. what
  * preprocess() hands to maskgen() and bitap() (preproce.c:221-341; symbols agrep.h:69-87): positions are counted
  * exactly as maskgen() counts them, literal runs are cut into k+1 disjoint anchors of 4 (3, 2) bytes.  Only for a
@@ -202,11 +182,7 @@ static int scan_and_replay(char old_D_pat[], const unsigned char *Pattern, int f
 	if (!recs) { ret = -1; errno = AGREP_ERROR; goto done; }
 	rc = agb_scan_host(p, hb + 1, n, AGB_WANT_RECORDS, recs, cap, &res);
 	if (rc) { ret = fail("scan"); goto done; }
-	if (LINENUM && res.n_records) {
-		int first_j = 0;
-		if (DELIMITER && n >= (size_t)L && memcmp(hb + 1, dpat, (size_t)L) == 0 && engine != AGB_ENGINE_ASEARCH0) first_j = -1;   /* bitap.c:151-156 */
-		fill_ordinals(hb, n, dpat, L, agb_pattern_desc(p)->delim_kind, recs, (size_t)res.n_records, first_j);
-	}
+	if (LINENUM && res.n_records) agb_fill_ordinals(p, hb + 1, n, recs, res.n_records);   /* j for output() (-n) */
 	for (i = 0; i < res.n_records; i++) {
 		if (fd == -1 && recs[i].end >= (long long)n) continue;      /* memory mode appends no delimiter (bitap.c:310-314) */
 		if (FILENAMEONLY && (NEW_FILE || !POST_FILTER)) {       /* bitap.c:184-210 */

@@ -229,7 +229,7 @@ static int has_border(const unsigned char *d, int L)
 /* derive the words from the positions (maskgen.c:218-257 with WORD = 64, LSB aligned) and the device-only constants */
 static int finish(build_t *b, agb_desc *d, const agb_options *o, const unsigned char *lut, char *err, size_t errlen)
 {
-	int M = b->n, p, c, r, L = d->L;
+	int M = b->n, p, c, L = d->L;
 	uint64_t sep = 0, endp;
 #define BITP(q) (1ull << (M - (q)))
 	d->M = M;
@@ -514,3 +514,31 @@ int agb_pattern_from_desc(const agb_desc *d, agb_pattern **out, char *err, size_
 
 void agb_pattern_free(agb_pattern *p) { free(p); }
 const agb_desc *agb_pattern_desc(const agb_pattern *p) { return p ? &p->d : NULL; }
+
+/* j of the reference's loops (bitap.c:178, asearch.c:120): incremented at every record close, the virtual '\n'
+ * included; pre-decremented when the text starts with the user's delimiter (bitap.c:151-156; asearch0() has no
+ * such correction, asearch.c:609-612).  Same greedy delimiter rule as the device (scan.cu delim_ends_at). */
+void agb_fill_ordinals(const agb_pattern *p, const void *h_text, uint64_t n, agb_record *records, uint64_t n_records)
+{
+	const agb_desc *d = &p->d; const unsigned char *t = (const unsigned char *)h_text;
+	const int L = d->L; uint64_t i = 0; long long j = 0, run = 0, q;
+	if (!n_records) return;
+	if (d->user_delim && d->engine != AGB_ENGINE_ASEARCH0 && n >= (uint64_t)L && memcmp(t, d->delim, (size_t)L) == 0) j = -1;
+	/* position q = -1 is the virtual '\n'; positions n .. n+L-1 are the delimiter appended at EOF */
+	for (q = -1; q < (long long)n + L && i < n_records; q++) {
+		int c = q < 0 ? '\n' : (q < (long long)n ? t[q] : d->delim[q - (long long)n]), e;
+		if (L == 1) e = c == d->delim[0];
+		else if (d->delim_kind == 1) { run = c == d->delim[0] ? run + 1 : 0; e = run > 0 && run % L == 0; }
+		else {
+			int m = 1, u;
+			for (u = 0; u < L && m; u++) {
+				long long at = q - u; int cc = at < -1 ? 256 : (at < 0 ? '\n' : (at < (long long)n ? t[at] : d->delim[at - (long long)n]));
+				if (cc != d->delim[L - 1 - u]) m = 0;
+			}
+			e = m;
+		}
+		if (!e) continue;
+		j++;
+		while (i < n_records && records[i].end + L - 1 == q) records[i++].ordinal = j;
+	}
+}

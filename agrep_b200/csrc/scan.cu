@@ -428,6 +428,7 @@ struct RecParams {
 	agb_record *records; uint64_t capacity;
 	unsigned long long *totals;  /* [0] matched, [1] flagged chunks, [2..10] level histogram, [12] candidates in the list */
 	const uint64_t *cand; uint64_t cand_cap;   /* list form: ordered flagged chunk numbers, totals[12] of them */
+	agb_record *cand_first;      /* list form: the first record each candidate reported in the count launch (most report 0 or 1) */
 	int emit;                    /* 0: count pass, 1: emit pass */
 	int levels;                  /* 1: best-match bookkeeping (smallest matching row) */
 	int want_level;              /* levels: report records whose smallest level <= want_level (-1: all matching) */
@@ -441,7 +442,8 @@ struct RecParams {
  * Returns the number of reported records; writes them at out_pos.. when write is set. */
 template <typename T, int NR, bool COSTS>
 __device__ __forceinline__ uint32_t chunk_records(const RecParams &P, const DevConsts<T> &C, RecShared<T, NR> &SH, Reader &R,
-                                                 const int64_t c, int64_t &done_until, const bool write, const uint64_t out_pos, const bool hist)
+                                                 const int64_t c, int64_t &done_until, const bool write, const uint64_t out_pos, const bool hist,
+                                                 agb_record *first_out = nullptr)
 {
 	const int L = C.L;
 	const int64_t n = (int64_t)P.n, lo = c * 16, hi = lo + 15;
@@ -505,6 +507,7 @@ __device__ __forceinline__ uint32_t chunk_records(const RecParams &P, const DevC
 					P.records[at] = rec;
 				}
 			}
+			if (first_out && cnt == 0) { first_out->begin = begin; first_out->end = end; first_out->ordinal = 0; first_out->level = level; first_out->pad = 0; }
 			cnt++;
 		}
 		s = close_at + 1;
@@ -797,10 +800,21 @@ k_records_list(const RecParams P)
 	const uint64_t i = (uint64_t)blockIdx.x * REC_THREADS + threadIdx.x;
 	uint32_t cnt = 0;
 	if (i < ncand) {
-		Reader R; R.init(P.text, P.n, SH.delim, C.L);
-		int64_t done_until = INT64_MIN;
-		cnt = chunk_records<T, NR, COSTS>(P, C, SH, R, (int64_t)P.cand[i], done_until, P.emit != 0, P.emit ? P.tile_offsets[i] : 0, !P.emit);
-		if (!P.emit) P.tile_counts[i] = cnt;
+		if (P.emit) {
+			/* emit launch: 0 records -> nothing; exactly 1 -> the count launch kept it; more (rare) -> walk again */
+			const uint32_t c0 = P.tile_counts[i];
+			if (c0 == 1) { const uint64_t at = P.tile_offsets[i]; if (at < P.capacity) P.records[at] = P.cand_first[i]; }
+			else if (c0 > 1) {
+				Reader R; R.init(P.text, P.n, SH.delim, C.L);
+				int64_t done_until = INT64_MIN;
+				chunk_records<T, NR, COSTS>(P, C, SH, R, (int64_t)P.cand[i], done_until, true, P.tile_offsets[i], false);
+			}
+		} else {
+			Reader R; R.init(P.text, P.n, SH.delim, C.L);
+			int64_t done_until = INT64_MIN;
+			cnt = chunk_records<T, NR, COSTS>(P, C, SH, R, (int64_t)P.cand[i], done_until, false, 0, true, P.cand_first ? &P.cand_first[i] : nullptr);
+			P.tile_counts[i] = cnt;
+		}
 	}
 	if (!P.emit) {
 		uint32_t sum = __reduce_add_sync(0xffffffffu, cnt);
@@ -888,6 +902,55 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *counts, uin
 	if (total && tid == 0) *total = s_carry;
 }
 
+/* two-level exclusive scan for long count arrays (the per-candidate counts of the list form):
+ * k_scan_partial sums blocks of 16384 counts, k_scan_tiles scans those sums, k_scan_apply finishes each block */
+#define SCAN_BLOCK 16384
+__global__ void __launch_bounds__(1024) k_scan_partial(const uint32_t *counts, uint64_t n, uint32_t *block_sums)
+{
+	__shared__ uint32_t s_w[32];
+	const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK;
+	uint32_t sum = 0;
+#pragma unroll
+	for (int j = 0; j < SCAN_BLOCK / 1024; j++) { const uint64_t i = base + (uint64_t)j * 1024 + threadIdx.x; if (i < n) sum += counts[i]; }
+	sum = __reduce_add_sync(0xffffffffu, sum);
+	if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sum;
+	__syncthreads();
+	if (threadIdx.x < 32) { uint32_t v = __reduce_add_sync(0xffffffffu, s_w[threadIdx.x]); if (threadIdx.x == 0) block_sums[blockIdx.x] = v; }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_apply(const uint32_t *counts, uint64_t n, const uint64_t *block_offsets, uint64_t *offsets)
+{
+	__shared__ unsigned long long s_warp[32];
+	__shared__ unsigned long long s_carry;
+	const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const uint64_t base0 = (uint64_t)blockIdx.x * SCAN_BLOCK;
+	if (tid == 0) s_carry = block_offsets[blockIdx.x];
+	__syncthreads();
+	for (uint64_t base = base0; base < base0 + SCAN_BLOCK && base < n; base += 4096) {
+		uint32_t v[4]; unsigned long long sum = 0;
+#pragma unroll
+		for (int j = 0; j < 4; j++) { const uint64_t i = base + (uint64_t)tid * 4 + j; v[j] = i < n ? counts[i] : 0u; sum += v[j]; }
+		unsigned long long inc = sum;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (uint32_t)o) inc += t; }
+		if (lane == 31) s_warp[wid] = inc;
+		__syncthreads();
+		if (wid == 0) {
+			unsigned long long w = s_warp[lane], winc = w;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= (uint32_t)o) winc += t; }
+			s_warp[lane] = winc - w;
+		}
+		__syncthreads();
+		unsigned long long run = s_carry + s_warp[wid] + (inc - sum);
+#pragma unroll
+		for (int j = 0; j < 4; j++) { const uint64_t i = base + (uint64_t)tid * 4 + j; if (i < n) offsets[i] = run; run += v[j]; }
+		__syncthreads();
+		if (tid == 1023) s_carry = run;
+		__syncthreads();
+	}
+}
+
 /* ================================================================================================
  * synthetic corpus
  * ============================================================================================== */
@@ -961,7 +1024,8 @@ extern "C" int agb_corpus_fill_host(const agb_corpus_spec *s, void *h_text)
 struct Workspace {               /* grow-only device scratch, one per device */
 	uint32_t *bitmap = nullptr; size_t bitmap_bytes = 0;
 	uint32_t *tile_counts = nullptr; uint64_t *tile_offsets = nullptr; size_t tiles = 0;
-	uint64_t *cand = nullptr; uint32_t *cand_counts = nullptr; uint64_t *cand_offsets = nullptr; size_t cand_cap = 0;
+	uint64_t *cand = nullptr; uint32_t *cand_counts = nullptr; uint64_t *cand_offsets = nullptr; agb_record *cand_first = nullptr; size_t cand_cap = 0;
+	uint32_t *scan_sums = nullptr; uint64_t *scan_offs = nullptr; size_t scan_cap = 0;
 	unsigned long long *totals = nullptr;          /* 16 counters */
 	unsigned long long *h_totals = nullptr;        /* pinned */
 	agb_desc *d_desc = nullptr; agb_desc h_desc_copy; bool desc_valid = false;
@@ -1014,7 +1078,15 @@ static int ws_cand_reserve(Workspace &W, size_t want_cand)
 		if (W.cand) cudaFree(W.cand);
 		if (W.cand_counts) cudaFree(W.cand_counts);
 		if (W.cand_offsets) cudaFree(W.cand_offsets);
-		W.cand = nullptr; W.cand_counts = nullptr; W.cand_offsets = nullptr; W.cand_cap = 0;
+		if (W.cand_first) cudaFree(W.cand_first);
+		if (W.scan_sums) cudaFree(W.scan_sums);
+		if (W.scan_offs) cudaFree(W.scan_offs);
+		W.cand = nullptr; W.cand_counts = nullptr; W.cand_offsets = nullptr; W.cand_first = nullptr; W.cand_cap = 0;
+		W.scan_sums = nullptr; W.scan_offs = nullptr; W.scan_cap = 0;
+		CUDA_TRY(cudaMalloc(&W.cand_first, want_cand * sizeof(agb_record)));
+		W.scan_cap = want_cand / SCAN_BLOCK + 2;
+		CUDA_TRY(cudaMalloc(&W.scan_sums, W.scan_cap * sizeof(uint32_t)));
+		CUDA_TRY(cudaMalloc(&W.scan_offs, W.scan_cap * sizeof(uint64_t)));
 		CUDA_TRY(cudaMalloc(&W.cand, want_cand * sizeof(uint64_t)));
 		CUDA_TRY(cudaMalloc(&W.cand_counts, want_cand * sizeof(uint32_t)));
 		CUDA_TRY(cudaMalloc(&W.cand_offsets, want_cand * sizeof(uint64_t)));
@@ -1285,11 +1357,19 @@ static int records_launch(const agb_desc &d, Workspace &W, const void *d_text, u
 			if (ncand == 0) return AGB_OK;
 			k_compact_write<<<(unsigned)blocks, COMPACT_THREADS, 0, st>>>(W.bitmap, n_words, W.tile_offsets, W.cand, W.cand_cap); g_launches++;
 			P.cand = W.cand; P.cand_cap = W.cand_cap; P.tile_counts = W.cand_counts; P.tile_offsets = W.cand_offsets;
+			P.cand_first = want_list ? W.cand_first : nullptr;
 			const unsigned grid = (unsigned)((ncand + REC_THREADS - 1) / REC_THREADS);
 			if (launch_records_list(d, P, grid, st)) return AGB_ERR_ARG;
 			CUDA_TRY(cudaGetLastError());
 			if (want_list) {
-				k_scan_tiles<<<1, 1024, 0, st>>>(W.cand_counts, W.cand_offsets, ncand, nullptr); g_launches++;
+				if (ncand <= 4 * SCAN_BLOCK) { k_scan_tiles<<<1, 1024, 0, st>>>(W.cand_counts, W.cand_offsets, ncand, nullptr); g_launches++; }
+				else {
+					const unsigned nb = (unsigned)((ncand + SCAN_BLOCK - 1) / SCAN_BLOCK);
+					k_scan_partial<<<nb, 1024, 0, st>>>(W.cand_counts, ncand, W.scan_sums);
+					k_scan_tiles<<<1, 1024, 0, st>>>(W.scan_sums, W.scan_offs, nb, nullptr);
+					k_scan_apply<<<nb, 1024, 0, st>>>(W.cand_counts, ncand, W.scan_offs, W.cand_offsets);
+					g_launches += 3;
+				}
 				P.emit = 1;
 				if (launch_records_list(d, P, grid, st)) return AGB_ERR_ARG;
 				CUDA_TRY(cudaGetLastError());

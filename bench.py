@@ -196,6 +196,52 @@ def cpu_baseline(ag, corpus_t, n_local):
             pass
 
 
+def secondary_workloads(ag, torch, corpus, n_local, stream):
+    """The other BASELINE.json configs, measured on the side (not the headline): count-only device scans, best of 3,
+    CUDA-event stage times from the library.  configs[0]-like: 'the' (sgrep/bm path, one line in three matches);
+    configs[2]: 32-char pattern, -3 -w, paragraph records on a 16 GiB paragraph corpus; configs[3]: -i -B sweep."""
+    out = []
+
+    def timed(pat, data_ptr, n, **kw):
+        p = ag.Pattern(pat, **kw)
+        p.scan_device(data_ptr, n, stream=stream)
+        best = None
+        for _ in range(3):
+            r = p.scan_device(data_ptr, n, stream=stream)
+            t = r.ms_front + r.ms_records
+            if best is None or t < best[0]:
+                best = (t, r)
+        t, r = best
+        d = p.desc
+        return {"pattern": pat, "options": {k: (v if isinstance(v, (int, str)) else int(v)) for k, v in kw.items()},
+                "bytes": n, "ms": t, "gb_s": n / t / 1e6, "ms_stage1": r.ms_front, "matched": int(r.n_matched),
+                "plan": "anchors" if d.plan == 1 else "all", "n_anchors": int(d.n_anchors)}
+    try:
+        o = timed("the", corpus.data_ptr(), n_local)
+        o["config"] = "configs[0] at scale: agrep -c the (sgrep/bm semantics)"
+        out.append(o)
+        n2 = min(16 << 30, n_local) // PAGE * PAGE
+        para = torch.empty(n2 + 4096, dtype=torch.uint8, device=corpus.device)
+        para[n2:].zero_()
+        p32 = "business give group toward young"
+        ag.corpus_device(para.data_ptr(), n2, stream=stream, paragraphs=True, needle=p32, needle_every=NEEDLE_EVERY, needle_maxedits=4)
+        torch.cuda.synchronize()
+        o = timed(p32, para.data_ptr(), n2, k=3, wordbound=True, linenum=True, delim="$$")
+        o["config"] = "configs[2]: 32-char pattern, -3 -w -d '$$' (M = 37: 64-bit rows; the reference refuses it)"
+        out.append(o)
+        del para
+        t0 = time.perf_counter()
+        best, res = ag.bestmatch_device("Becuase Each Just Th", corpus.data_ptr(), n_local, stream=stream, nocase=1)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) * 1e3
+        out.append({"config": "configs[3]: -i -B best-match sweep (agrep.c:3582-3728), 20-char mixed-case pattern",
+                    "pattern": "Becuase Each Just Th", "bytes": n_local, "ms": dt, "gb_s": n_local / dt / 1e6,
+                    "best_k": int(best), "matched": int(res.n_matched)})
+    except Exception as e:      # a secondary measurement must never take the headline down
+        out.append({"error": repr(e)})
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -310,6 +356,10 @@ def main():
         if cpu_count is not None and int(r.n_matched) != cpu_count:
             raise SystemExit("PARITY FAILURE: reference counted %d records in the sample, CUDA path %d" % (cpu_count, r.n_matched))
 
+    secondary = None
+    if rank == 0 and world == 1 and os.environ.get("AGB_BENCH_SECONDARY", "1") != "0":
+        secondary = secondary_workloads(ag, torch, corpus, n_local, stream)
+
     if rank == 0:
         peak, peak_src = peaks()
         fm = statistics.mean(front_ms)
@@ -338,6 +388,8 @@ def main():
         }
         if cpu:
             out["cpu_baseline"] = cpu
+        if secondary:
+            out["secondary_workloads"] = secondary
         print(json.dumps(out))
     if dist:
         dist.destroy_process_group()

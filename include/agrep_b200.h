@@ -96,7 +96,8 @@ typedef struct agb_pattern agb_pattern;       /* opaque: agb_desc + bookkeeping 
  *   begin   = offset of lasti: first byte of the delimiter that closed the previous record; -1 for the
  *             virtual '\n' in front of the text (bitap.c:140), 0 when a user delimiter has not been seen yet
  *   end     = offset of print_end + 1 = first byte of the delimiter that closes this record
- *   ordinal = j at output() time; -n prints j-1 (agrep.c:3878); 0 unless AGB_WANT_ORDINALS
+ *   ordinal = j at output() time; -n prints j-1 (agrep.c:3878); 0 from the scan calls, filled by
+ *             agb_fill_ordinals() on the host copy of the text when -n is wanted
  *   level   = smallest matching error level in best-match scans, else k                                */
 typedef struct agb_record {
 	int64_t begin;
@@ -106,7 +107,7 @@ typedef struct agb_record {
 	int32_t pad;
 } agb_record;
 
-enum { AGB_WANT_COUNT = 0, AGB_WANT_RECORDS = 1, AGB_WANT_ORDINALS = 2, AGB_WANT_LEVELS = 4 };
+enum { AGB_WANT_COUNT = 0, AGB_WANT_RECORDS = 1, AGB_WANT_LEVELS = 4 };
 
 typedef struct agb_result {
 	uint64_t n_matched;       /* num_of_matched for this text                                 */
@@ -139,6 +140,11 @@ int  agb_scan_host(const agb_pattern *p, const void *h_text, uint64_t n, int wan
 
 /* file descriptor: read(2) loop into the pinned ring, as agb_scan_host */
 int  agb_scan_fd(const agb_pattern *p, int fd, int want, agb_record *records, uint64_t capacity, agb_result *res);
+
+/* j of every record in `records` (ordered, as returned by a scan of h_text[0..n)): the number of record closes
+ * up to and including its own (bitap.c:178), with the file-starts-with-the-delimiter correction of bitap.c:151-156.
+ * A host walk over the delimiters, only needed for -n. */
+void agb_fill_ordinals(const agb_pattern *p, const void *h_text, uint64_t n, agb_record *records, uint64_t n_records);
 
 /* the -B sweep of agrep.c:3582-3728 as ONE extra pass: smallest k in 1..min(M-1,8) with a match */
 int  agb_bestmatch_device(const char *pattern, const agb_options *opt, const void *d_text, uint64_t n,

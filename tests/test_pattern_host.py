@@ -124,3 +124,24 @@ def test_corpus_generator_properties():
     assert c.count(b"because each") >= 4
     p = ag.corpus_host(16 * 4096, paragraphs=True)
     assert b"\n\n" in p
+
+
+@pytest.mark.parametrize("pattern,kw,corpus_kw", [
+    ("because each", dict(k=2, linenum=1), dict(nlines=2000, seed=31)),
+    ("the", dict(k=0, linenum=1, wordbound=1), dict(nlines=800, seed=32, trailing_newline=False)),
+    ("state", dict(k=1, linenum=1, delim="$$"), dict(nlines=1500, seed=33, paragraphs=True)),
+    ("world", dict(k=1, linenum=1, delim="the"), dict(nlines=600, seed=34)),
+    ("governmental", dict(k=5, linenum=1), dict(nlines=1500, seed=35)),
+])
+def test_fill_ordinals_reproduces_j(pattern, kw, corpus_kw):
+    """agb_fill_ordinals() (host helper for -n) against the oracle's j, which is pinned to the reference's -n output"""
+    data = _corpus.make_text(**corpus_kw)
+    a = _oracle.compile(pattern, **kw)
+    cnt, recs = _oracle.scan(a, data)
+    assert cnt > 0
+    p = ag.Pattern(pattern, **kw)
+    arr = (_lib.Record * cnt)()
+    for i, (b, e, j) in enumerate(recs):
+        arr[i].begin, arr[i].end = b, e
+    _lib.lib().agb_fill_ordinals(p._h, data, len(data), arr, cnt)
+    assert [arr[i].ordinal for i in range(cnt)] == [j for _, _, j in recs]
