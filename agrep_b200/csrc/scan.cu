@@ -309,6 +309,7 @@ __device__ __forceinline__ bool match_cond(T r, const DevConsts<T> &C)
  * ============================================================================================== */
 #define REFINE_THREADS 128
 #define REFINE_MAXG 8
+#define REFINE_DEFER 96          /* deferred windows per warp */
 struct RefineParams {
 	const uint8_t *text; uint32_t *bitmap; uint64_t n, n_chunks, n_words;
 	const agb_desc *desc;
@@ -316,101 +317,265 @@ struct RefineParams {
 	int gb, ng;                  /* groups staged before the chunk, groups staged in total (<= REFINE_MAXG) */
 	int lo_off, hi_off;          /* the windows of a chunk at byte `base` lie inside [base - lo_off, base + hi_off) */
 	uint32_t anchor[AGB_MAXANCHOR]; int32_t off[AGB_MAXANCHOR];
+	uint32_t coef[AGB_MAXANCHOR]; uint32_t one, scale; int poly;   /* stage 1's polynomial, to spot the candidate windows cheaply */
 };
 
+/* the recurrence over one window: rows started at Init[0]; the end bits of the last row are sticky (Init1 holds
+ * them, maskgen.c:232), so looking at it after the walk is enough.  Called by all lanes together. */
 template <typename T, int NR, bool COSTS>
+__device__ __forceinline__ bool window_passes(const uint8_t *bytes, const bool run, const int wlen, const T init0,
+                                              const T *mask, const DevConsts<T> &C)
+{
+	T S[NR];
+#pragma unroll
+	for (int r = 0; r < NR; r++) S[r] = init0;
+	for (int q = 0; q < wlen; q++) {
+		const int c = run ? bytes[q] : 0;
+		rows_step<T, NR, COSTS>(S, mask[c], C);
+	}
+	return run && (S[NR - 1] & C.endpos) != 0;
+}
+
+/* The same walk on the bit-reversed automaton (32-bit rows, unit costs): every word -- masks, Init0/1, NO_ERR,
+ * endposition -- is mirrored with __brev once, which turns the recurrence's `>> 1` into `<< 1`.  A left shift by
+ * one is a multiply by two, and IMAD runs on the FMA pipe, which this kernel leaves idle, instead of the ALU pipe
+ * that bounds it: 5 ALU + 2 FMA operations per row and byte instead of 7 ALU. */
+__device__ __forceinline__ uint32_t shl1_fma(uint32_t x)
+{
+	uint32_t r;
+	asm("mad.lo.u32 %0, %1, 2, 0;" : "=r"(r) : "r"(x));
+	return r;
+}
+template <int NR>
+__device__ __forceinline__ bool window_passes_mirror(const uint8_t *bytes, const bool run, const int wlen, const uint32_t init0,
+                                                     const uint32_t *mask, const uint32_t init1, const uint32_t noerr, const uint32_t endpos)
+{
+	uint32_t S[NR];
+#pragma unroll
+	for (int r = 0; r < NR; r++) S[r] = init0;
+	for (int q = 0; q < wlen; q++) {
+		const uint32_t cm = mask[run ? bytes[q] : 0];
+		uint32_t prevB = S[0];
+		uint32_t prevA = (shl1_fma(prevB) & cm) | (init1 & prevB);
+#pragma unroll
+		for (int r = 1; r < NR; r++) {
+			const uint32_t b = S[r];
+			const uint32_t a = (shl1_fma(b) & cm) | (init1 & b) | prevB | (shl1_fma(prevA | prevB) & noerr);
+			S[r - 1] = prevA; prevA = a; prevB = b;
+		}
+		S[NR - 1] = prevA;
+	}
+	return run && (S[NR - 1] & endpos) != 0;
+}
+
+/* which of the 16 windows of a chunk start an anchor: bit (32 + s - off_a) per hit, i.e. the distinct WINDOW STARTS
+ * of the pattern around this chunk (two anchors of one occurrence, "beca" and "use " inside "because ", coincide).
+ * POLY: stage 1's polynomial finds the (rare) windows worth comparing with IMADs on the otherwise idle FMA pipe. */
+template <int NA, bool POLY>
+__device__ __forceinline__ uint64_t window_starts(const uint32_t *cw, const RefineParams &P)
+{
+	const uint32_t x0 = cw[0] | P.fold, x1 = cw[1] | P.fold, x2 = cw[2] | P.fold, x3 = cw[3] | P.fold, x4 = cw[4] | P.fold;
+	uint32_t wv[16];
+	wv[0] = x0; wv[1] = __funnelshift_r(x0, x1, 8); wv[2] = __funnelshift_r(x0, x1, 16); wv[3] = __funnelshift_r(x0, x1, 24);
+	wv[4] = x1; wv[5] = __funnelshift_r(x1, x2, 8); wv[6] = __funnelshift_r(x1, x2, 16); wv[7] = __funnelshift_r(x1, x2, 24);
+	wv[8] = x2; wv[9] = __funnelshift_r(x2, x3, 8); wv[10] = __funnelshift_r(x2, x3, 16); wv[11] = __funnelshift_r(x2, x3, 24);
+	wv[12] = x3; wv[13] = __funnelshift_r(x3, x4, 8); wv[14] = __funnelshift_r(x3, x4, 16); wv[15] = __funnelshift_r(x3, x4, 24);
+	uint64_t starts = 0;
+	if (POLY) {
+		uint32_t zm = 0;
+#pragma unroll
+		for (int s16 = 0; s16 < 16; s16++) {
+			uint32_t r = wv[s16] * P.one + P.coef[NA - 1];
+#pragma unroll
+			for (int i = NA - 2; i >= 0; i--) r = r * wv[s16] + P.coef[i];
+			if (r * P.scale == 0) zm |= 1u << s16;
+		}
+		for (; zm; zm &= zm - 1) {                             /* usually one bit */
+			const int s16 = __ffs(zm) - 1;
+			const uint32_t lo = cw[s16 >> 2] | P.fold, hi = cw[(s16 >> 2) + 1] | P.fold;     /* rebuilt: wv[] stays in registers */
+			const uint32_t wsel = __funnelshift_r(lo, hi, (s16 & 3) * 8) & P.amask;
+#pragma unroll
+			for (int a = 0; a < NA; a++) if (wsel == P.anchor[a]) starts |= 1ull << (32 + s16 - P.off[a]);
+		}
+	} else {
+#pragma unroll
+		for (int a = 0; a < NA; a++) {
+			const uint32_t A = P.anchor[a];
+			uint32_t m = 0;
+#pragma unroll
+			for (int s16 = 0; s16 < 16; s16++) if ((wv[s16] & P.amask) == A) m |= 1u << s16;
+			starts |= (uint64_t)m << (32 - P.off[a]);              /* off <= 31: refine_geometry() */
+		}
+	}
+	return starts;
+}
+
+template <bool POLY>
+__device__ __forceinline__ uint64_t window_starts_na(const uint32_t *cw, const RefineParams &P)
+{
+	switch (P.na) {
+	case 1: return window_starts<1, POLY>(cw, P);  case 2: return window_starts<2, POLY>(cw, P);
+	case 3: return window_starts<3, POLY>(cw, P);  case 4: return window_starts<4, POLY>(cw, P);
+	case 5: return window_starts<5, POLY>(cw, P);  case 6: return window_starts<6, POLY>(cw, P);
+	case 7: return window_starts<7, POLY>(cw, P);  case 8: return window_starts<8, POLY>(cw, P);
+	default: return window_starts<9, POLY>(cw, P);
+	}
+}
+
+/* Streaming form: every warp owns a contiguous range of bitmap words.  It appends the flagged chunks of 32 words at
+ * a time to a ring and, whenever 32 are waiting, judges them together: stage the 16-byte groups around the chunk
+ * in shared memory, find the window starts, walk the first window; a chunk whose first window fails loses its bit
+ * at once (atomicAnd on the bitmap), its other windows (3 % of the chunks have any) go to a second ring and are
+ * judged 32 at a time later -- a pass sets the bit again (atomicOr; same warp, program order).  Rings are only
+ * flushed partially at the very end of the warp's range, so the lanes stay full. */
+#define REFINE_RING  1088         /* >= 31 left over + 1024 new per refill */
+
+/* take up to 32 chunks off the ring and start loading the text around them (NGC x 16 bytes per lane, in registers) */
+template <int NGC>
+__device__ __forceinline__ void refine_pop(const RefineParams &P, const uint32_t *ring, uint32_t &head, uint32_t &count, uint32_t lane,
+                                           uint64_t chunk0, uint64_t &chunk, bool &keep, uint4 (&nx)[NGC])
+{
+	const uint32_t m = count < 32 ? count : 32;
+	const bool active = lane < m;
+	chunk = chunk0 + (active ? ring[head + lane] : 0u);
+	head += m; count -= m;
+	const int64_t base = (int64_t)chunk * 16;
+	/* windows that touch the virtual '\n', the appended delimiter or the end of the buffer are not judged here */
+	keep = !active || (base - P.lo_off < 0 || (uint64_t)(base + P.hi_off + 16) > P.n || chunk + 2 >= P.n_chunks);
+	if (!keep) {
+		const uint4 *src = reinterpret_cast<const uint4 *>(P.text) + ((int64_t)chunk - P.gb);
+#pragma unroll
+		for (int gi = 0; gi < NGC; gi++) if (gi < P.ng) nx[gi] = __ldg(src + gi);
+	}
+}
+
+/* append the flagged chunks of the next 32 bitmap words (one per lane, loaded one group ahead) to the ring */
+__device__ __forceinline__ void refine_refill(const RefineParams &P, uint32_t *ring, uint32_t &head, uint32_t &count, uint32_t lane,
+                                              uint64_t &g, uint64_t g_begin, uint64_t g_end, uint32_t &next_word)
+{
+	const uint32_t word = next_word;
+	if (g + 1 < g_end) { const uint64_t w = (g + 1) * 32 + lane; next_word = (w < P.n_words) ? P.bitmap[w] : 0u; }
+	uint32_t c = __popc(word), pre = c;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= (uint32_t)o) pre += v; }
+	const uint32_t total = __shfl_sync(0xffffffffu, pre, 31);
+	pre -= c;
+	const uint32_t rel0 = (uint32_t)((g - g_begin) * 1024) + lane * 32;
+	if (head) {   /* the (< 32) entries left over move to the front: the ring is used linearly */
+		const uint32_t v = lane < count ? ring[head + lane] : 0u;
+		__syncwarp();
+		if (lane < count) ring[lane] = v;
+		head = 0;
+	}
+	for (uint32_t b = word; b; b &= b - 1) { ring[count + pre] = rel0 + (uint32_t)(__ffs(b) - 1); pre++; }
+	count += total;
+	g++;
+	__syncwarp();
+}
+
+template <typename T, int NR, bool COSTS, int NGC>
 __global__ void __launch_bounds__(REFINE_THREADS)
 k_refine(const RefineParams P)
 {
+	constexpr bool MIRROR = (sizeof(T) == 4) && !COSTS;     /* window_passes_mirror() */
+	extern __shared__ __align__(16) uint32_t s_stage[];     /* REFINE_THREADS x (ng*4 + 1) words */
 	__shared__ RecShared<T, NR> SH;
-	__shared__ uint16_t s_queue[REFINE_THREADS / 32][1024];
-	__shared__ uint32_t s_keep[REFINE_THREADS / 32][32];
-	__shared__ __align__(16) uint32_t s_stage[REFINE_THREADS * (REFINE_MAXG * 4 + 1)];
+	__shared__ uint32_t s_ring[REFINE_THREADS / 32][REFINE_RING];
+	__shared__ unsigned long long s_defer[REFINE_THREADS / 32][REFINE_DEFER];
 	DevConsts<T> C;
 	shared_init<T, NR>(SH, C, P.desc, REFINE_THREADS);
 	const T init0 = (T)P.desc->init0;
+	uint32_t m_init0 = 0, m_init1 = 0, m_noerr = 0, m_endpos = 0;
+	if (MIRROR) {
+		for (int i = threadIdx.x; i < 257; i += REFINE_THREADS) SH.mask[i] = (T)__brev((uint32_t)SH.mask[i]);
+		m_init0 = __brev((uint32_t)init0); m_init1 = __brev((uint32_t)C.init1); m_noerr = __brev((uint32_t)C.noerr); m_endpos = __brev((uint32_t)C.endpos);
+		__syncthreads();
+	}
 	const int pat_len = P.desc->pat_len, k = C.k, wlen = pat_len + 2 * k;
-	const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5, lt_mask = (1u << lane) - 1u;
 	const int stride_w = P.ng * 4 + 1;                      /* odd number of words: lanes hit different banks */
 	uint32_t *my_stage = s_stage + threadIdx.x * stride_w;
 	const uint8_t *my_bytes = reinterpret_cast<const uint8_t *>(my_stage);
+	const int ws0 = P.gb * 16 - 32 - k;                     /* window offset in the staged bytes = ws0 + start bit */
+	uint32_t *ring = s_ring[wib];
+	unsigned long long *defer = s_defer[wib];
+#define REFINE_WINDOW(ptr, run) (MIRROR ? window_passes_mirror<NR>((ptr), (run), wlen, m_init0, reinterpret_cast<const uint32_t *>(SH.mask), m_init1, m_noerr, m_endpos) \
+                                        : window_passes<T, NR, COSTS>((ptr), (run), wlen, init0, SH.mask, C))
+
+	/* this warp's groups of 32 bitmap words: [g_begin, g_end) */
 	const uint64_t warp = ((uint64_t)blockIdx.x * REFINE_THREADS + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * REFINE_THREADS) >> 5;
-	const uint64_t n_groups = (P.n_words + 31) / 32;
-	for (uint64_t g = warp; g < n_groups; g += nwarps) {
-		const uint64_t w = g * 32 + lane;
-		const uint32_t word = (w < P.n_words) ? P.bitmap[w] : 0u;
-		if (__ballot_sync(0xffffffffu, word != 0) == 0) continue;
-		/* compact the flagged chunks of these 32 words into the warp's queue */
-		uint32_t cnt = __popc(word), pre = cnt;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= (uint32_t)o) pre += v; }
-		const uint32_t total = __shfl_sync(0xffffffffu, pre, 31);
-		pre -= cnt;
-		for (uint32_t b = word; b; b &= b - 1) s_queue[wib][pre++] = (uint16_t)(lane * 32 + (__ffs(b) - 1));
-		s_keep[wib][lane] = 0;
-		__syncwarp();
-		for (uint32_t q0 = 0; q0 < total; q0 += 32) {
-			const uint32_t qi = q0 + lane;
-			const bool active = qi < total;
-			const uint32_t cidx = active ? s_queue[wib][qi] : 0;
-			const int64_t chunk = (int64_t)(g * 1024 + cidx), base = chunk * 16;
-			/* windows that touch the virtual '\n', the appended delimiter or the end of the buffer are not judged here */
-			bool keep = active && (base - P.lo_off < 0 || (uint64_t)(base + P.hi_off + 16) > P.n || (uint64_t)chunk + 2 >= P.n_chunks);
-			/* distinct window starts of this chunk: bit (32 + s - off_a) for a hit of anchor a at window s.  Two anchors
-			 * of one occurrence of the pattern ("beca" and "use " inside "because ") give the same start: judged once. */
-			uint64_t starts = 0;
-			if (active && !keep) {
-				const uint4 *src = reinterpret_cast<const uint4 *>(P.text) + (chunk - P.gb);
+	const uint64_t n_groups = (P.n_words + 31) / 32, per = (n_groups + nwarps - 1) / nwarps;
+	const uint64_t g_begin = warp * per, g_end = (g_begin + per < n_groups) ? g_begin + per : n_groups;
+	if (g_begin >= g_end) return;
+	const uint64_t chunk0 = g_begin * 1024;                 /* ring entries are chunk numbers relative to this */
+
+	uint32_t head = 0, count = 0, ndefer = 0;               /* warp-uniform */
+	uint64_t g = g_begin;
+	uint32_t next_word = (g * 32 + lane < P.n_words) ? P.bitmap[g * 32 + lane] : 0u;     /* one group ahead */
+	bool have = false;                                      /* a batch is popped and its text on the way in nx[] */
+	uint64_t chunk = 0; bool keep = true;
+	uint4 nx[NGC];
+	for (;;) {
+		/* ---- 32 deferred windows (or what is left of them at the very end) ---- */
+		if (ndefer >= 32 || (ndefer && !have && count == 0 && g >= g_end)) {
+			const uint32_t m = ndefer < 32 ? ndefer : 32;
+			const bool run = lane < m;
+			const unsigned long long e = run ? defer[ndefer - m + lane] : 0ull;
+			const uint64_t dchunk = chunk0 + (uint32_t)(e >> 6);
+			if (run) {
+				const uint4 *src = reinterpret_cast<const uint4 *>(P.text) + ((int64_t)dchunk - P.gb);
 				for (int gi = 0; gi < P.ng; gi++) {
 					const uint4 v = __ldg(src + gi);
 					my_stage[gi * 4 + 0] = v.x; my_stage[gi * 4 + 1] = v.y; my_stage[gi * 4 + 2] = v.z; my_stage[gi * 4 + 3] = v.w;
 				}
-				/* which of the 16 windows of the chunk equals which anchor (exactly stage 1's question) */
-				const uint32_t *cw = my_stage + P.gb * 4;
-				const uint32_t x0 = cw[0] | P.fold, x1 = cw[1] | P.fold, x2 = cw[2] | P.fold, x3 = cw[3] | P.fold, x4 = cw[4] | P.fold;
-				uint32_t wv[16];
-				wv[0] = x0; wv[1] = __funnelshift_r(x0, x1, 8); wv[2] = __funnelshift_r(x0, x1, 16); wv[3] = __funnelshift_r(x0, x1, 24);
-				wv[4] = x1; wv[5] = __funnelshift_r(x1, x2, 8); wv[6] = __funnelshift_r(x1, x2, 16); wv[7] = __funnelshift_r(x1, x2, 24);
-				wv[8] = x2; wv[9] = __funnelshift_r(x2, x3, 8); wv[10] = __funnelshift_r(x2, x3, 16); wv[11] = __funnelshift_r(x2, x3, 24);
-				wv[12] = x3; wv[13] = __funnelshift_r(x3, x4, 8); wv[14] = __funnelshift_r(x3, x4, 16); wv[15] = __funnelshift_r(x3, x4, 24);
-#pragma unroll
-				for (int s = 0; s < 16; s++) wv[s] &= P.amask;
-				for (int a = 0; a < P.na; a++) {
-					const uint32_t A = P.anchor[a];
-					uint32_t m = 0;
-#pragma unroll
-					for (int s = 0; s < 16; s++) m |= (wv[s] == A ? 1u : 0u) << s;
-					starts |= (uint64_t)m << (32 - P.off[a]);          /* off <= 31 is guaranteed by refine_geometry() */
-				}
 			}
-			/* walk the windows: round r takes every lane's r-th distinct start, so the lanes stay together */
-			while (__ballot_sync(0xffffffffu, starts != 0 && !keep)) {
-				const bool run = starts != 0 && !keep;
-				int64_t ws = 0;
-				if (run) {
-					const int bit = __ffsll((long long)starts) - 1;
-					starts &= starts - 1;
-					ws = (int64_t)P.gb * 16 + (bit - 32) - k;          /* offset inside this lane's staged bytes */
-				}
-				T S[NR];
-#pragma unroll
-				for (int r = 0; r < NR; r++) S[r] = init0;
-				T seen = 0;
-				for (int q = 0; q < wlen; q++) {
-					const int c = run ? my_bytes[ws + q] : 0;
-					rows_step<T, NR, COSTS>(S, SH.mask[c], C);
-					seen |= S[NR - 1];
-				}
-				if (run && (seen & C.endpos) != 0) keep = true;
-			}
-			if (keep) atomicOr(&s_keep[wib][cidx >> 5], 1u << (cidx & 31));
+			if (REFINE_WINDOW(my_bytes + ws0 + (int)(e & 63ull), run))
+				atomicOr(&P.bitmap[dchunk >> 5], 1u << (dchunk & 31));
+			ndefer -= m;
 			__syncwarp();
+			continue;
 		}
-		__syncwarp();
-		const uint32_t nw = s_keep[wib][lane];
-		if (w < P.n_words && nw != word) P.bitmap[w] = nw;
+		if (!have) {
+			while (count < 32 && g < g_end) refine_refill(P, ring, head, count, lane, g, g_begin, g_end, next_word);
+			if (count == 0) break;                              /* range done, rings empty */
+			refine_pop<NGC>(P, ring, head, count, lane, chunk0, chunk, keep, nx);      /* (a partial batch only at the very end) */
+		}
+		/* ---- the batch in nx[]: into shared memory; the next one starts loading while this one is judged ---- */
+		const uint64_t cchunk = chunk; const bool ckeep = keep;
+		if (!ckeep) {
+#pragma unroll
+			for (int gi = 0; gi < NGC; gi++) if (gi < P.ng) {
+				my_stage[gi * 4 + 0] = nx[gi].x; my_stage[gi * 4 + 1] = nx[gi].y; my_stage[gi * 4 + 2] = nx[gi].z; my_stage[gi * 4 + 3] = nx[gi].w;
+			}
+		}
+		while (count < 32 && g < g_end) refine_refill(P, ring, head, count, lane, g, g_begin, g_end, next_word);
+		have = count != 0;                                      /* fewer than 32 only when the range is exhausted */
+		if (have) refine_pop<NGC>(P, ring, head, count, lane, chunk0, chunk, keep, nx);
+		uint64_t starts = 0;
+		if (!ckeep) starts = P.poly ? window_starts_na<true>(my_stage + P.gb * 4, P) : window_starts_na<false>(my_stage + P.gb * 4, P);
+		bool pass = ckeep;
+		{
+			const bool run = starts != 0;
+			const bool ok = REFINE_WINDOW(my_bytes + ws0 + (run ? __ffsll((long long)starts) - 1 : 32), run);
+			if (!ckeep && !ok) atomicAnd(&P.bitmap[cchunk >> 5], ~(1u << (cchunk & 31)));      /* undecided chunks lose the bit now ... */
+			if (ok) pass = true;
+		}
+		/* ... and get it back if one of their other windows passes later */
+		uint64_t rest = (starts && !pass) ? (starts & (starts - 1)) : 0ull;
+		for (;;) {
+			const uint32_t pend = __ballot_sync(0xffffffffu, rest != 0);
+			if (!pend) break;
+			if (ndefer + __popc(pend) > REFINE_DEFER) break;          /* ring full: see below */
+			if (rest != 0) {
+				defer[ndefer + __popc(pend & lt_mask)] = ((unsigned long long)(uint32_t)(cchunk - chunk0) << 6) | (unsigned long long)(__ffsll((long long)rest) - 1);
+				rest &= rest - 1;
+			}
+			ndefer += __popc(pend);
+		}
+		if (rest != 0) atomicOr(&P.bitmap[cchunk >> 5], 1u << (cchunk & 31));     /* could not be queued: keep (stage 2 is exact) */
 		__syncwarp();
 	}
+#undef REFINE_WINDOW
 }
 
 /* ================================================================================================
@@ -1247,26 +1412,32 @@ static int launch_dense(const agb_desc &d, const RecParams &P, unsigned grid, cu
 	return narrow ? launch_dense_t<uint32_t, false>(d.nrows, P, grid, st) : launch_dense_t<uint64_t, false>(d.nrows, P, grid, st);
 }
 
+template <typename T, int NR, bool COSTS>
+static void launch_refine_one(const RefineParams &P, unsigned grid, cudaStream_t st)
+{
+	const size_t smem = (size_t)REFINE_THREADS * (P.ng * 4 + 1) * sizeof(uint32_t);
+	if (P.ng <= 4) k_refine<T, NR, COSTS, 4><<<grid, REFINE_THREADS, smem, st>>>(P);
+	else k_refine<T, NR, COSTS, REFINE_MAXG><<<grid, REFINE_THREADS, smem, st>>>(P);
+}
 template <typename T, bool COSTS>
 static int launch_refine_t(int nrows, const RefineParams &P, unsigned grid, cudaStream_t st)
 {
 	switch (nrows) {
-	case 1: k_refine<T, 1, COSTS><<<grid, REFINE_THREADS, 0, st>>>(P); break;
-	case 2: k_refine<T, 2, COSTS><<<grid, REFINE_THREADS, 0, st>>>(P); break;
-	case 3: k_refine<T, 3, COSTS><<<grid, REFINE_THREADS, 0, st>>>(P); break;
-	case 4: k_refine<T, 4, COSTS><<<grid, REFINE_THREADS, 0, st>>>(P); break;
-	case 5: k_refine<T, 5, COSTS><<<grid, REFINE_THREADS, 0, st>>>(P); break;
-	case 6: k_refine<T, 6, COSTS><<<grid, REFINE_THREADS, 0, st>>>(P); break;
-	case 7: k_refine<T, 7, COSTS><<<grid, REFINE_THREADS, 0, st>>>(P); break;
-	case 8: k_refine<T, 8, COSTS><<<grid, REFINE_THREADS, 0, st>>>(P); break;
-	case 9: k_refine<T, 9, COSTS><<<grid, REFINE_THREADS, 0, st>>>(P); break;
+	case 1: launch_refine_one<T, 1, COSTS>(P, grid, st); break;
+	case 2: launch_refine_one<T, 2, COSTS>(P, grid, st); break;
+	case 3: launch_refine_one<T, 3, COSTS>(P, grid, st); break;
+	case 4: launch_refine_one<T, 4, COSTS>(P, grid, st); break;
+	case 5: launch_refine_one<T, 5, COSTS>(P, grid, st); break;
+	case 6: launch_refine_one<T, 6, COSTS>(P, grid, st); break;
+	case 7: launch_refine_one<T, 7, COSTS>(P, grid, st); break;
+	case 8: launch_refine_one<T, 8, COSTS>(P, grid, st); break;
+	case 9: launch_refine_one<T, 9, COSTS>(P, grid, st); break;
 	default: return -1;
 	}
 	g_launches++;
 	return 0;
 }
 
-/* can stage 1.5 judge this plan?  (single pattern without '#', windows that fit the staging area) */
 static bool refine_geometry(const agb_desc &d, RefineParams &P)
 {
 	if (!front_usable(d) || !d.refine) return false;
@@ -1289,6 +1460,13 @@ static int refine_launch(const agb_desc &d, Workspace &W, const void *d_text, ui
 	P.text = (const uint8_t *)d_text; P.bitmap = W.bitmap; P.n = n; P.n_chunks = n_chunks; P.n_words = n_words; P.desc = W.d_desc;
 	P.fold = d.anchor_fold; P.amask = d.anchor_mask; P.na = d.n_anchors;
 	for (int i = 0; i < d.n_anchors; i++) { P.anchor[i] = d.anchor[i]; P.off[i] = d.anchor_off[i]; }
+	{   /* stage 1's polynomial over the anchors, usable when they are pairwise distinct and pass its false-positive guard */
+		bool distinct = true;
+		for (int i = 0; i < d.n_anchors; i++) for (int j = 0; j < i; j++) if (d.anchor[i] == d.anchor[j]) distinct = false;
+		P.one = 1; P.scale = 1;
+		for (int i = d.anchor_len; i < 4; i++) P.scale <<= 8;
+		P.poly = (distinct && poly_setup(d.anchor, d.n_anchors, 8 * d.anchor_len, P.coef)) ? 1 : 0;
+	}
 	const uint64_t groups = (n_words + 31) / 32;
 	unsigned grid = (unsigned)std::min<uint64_t>((groups + 3) / 4, (uint64_t)W.sm_count * 16);
 	if (!grid) grid = 1;
