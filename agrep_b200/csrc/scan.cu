@@ -198,6 +198,22 @@ k_front(const FrontParams P)
 /* ================================================================================================
  * shared device pieces of stages 1.5 and 2: the recurrence, the match test, the text reader
  * ============================================================================================== */
+/* 32-bit rows run on the MIRRORED automaton: every word that holds pattern positions -- character masks, Init0/1,
+ * NO_ERR_MASK, endposition, D_endpos, the reset and start rows -- is bit-reversed (__brev) when it is loaded, which
+ * turns the recurrence's `>> 1` into `<< 1` and changes nothing else (the kernels only ever AND/OR/compare these
+ * words).  A left shift by one is a multiply by two, and IMAD runs on the FMA pipe, which these kernels leave idle,
+ * instead of the ALU pipe that bounds them: 5 ALU + 2 FMA operations per row and byte instead of 7 ALU.
+ * 64-bit rows (M > 31) stay as the reference has them. */
+template <typename T> __device__ __forceinline__ T mirror(T x) { return x; }
+template <> __device__ __forceinline__ uint32_t mirror<uint32_t>(uint32_t x) { return __brev(x); }
+template <typename T> __device__ __forceinline__ T shift1(T x) { return x >> 1; }
+template <> __device__ __forceinline__ uint32_t shift1<uint32_t>(uint32_t x)
+{
+	uint32_t r;
+	asm("mad.lo.u32 %0, %1, 2, 0;" : "=r"(r) : "r"(x));
+	return r;
+}
+
 template <typename T> struct DevConsts {
 	T init1, noerr, endpos, dendpos;
 	int L, k, and_mode, inverse, kind, ci, cs, cd;
@@ -214,12 +230,12 @@ template <typename T, int NR> struct RecShared {
 template <typename T, int NR>
 __device__ __forceinline__ void shared_init(RecShared<T, NR> &S, DevConsts<T> &C, const agb_desc *D, int nthreads)
 {
-	for (int i = threadIdx.x; i < 256; i += nthreads) S.mask[i] = (T)D->mask[i];
+	for (int i = threadIdx.x; i < 256; i += nthreads) S.mask[i] = mirror<T>((T)D->mask[i]);
 	if (threadIdx.x == 0) { S.mask[256] = 0; S.start_closes = D->start_closes; }
-	if (threadIdx.x < NR) { S.reset[threadIdx.x] = (T)D->reset[threadIdx.x]; S.start[threadIdx.x] = (T)D->start[threadIdx.x]; }
+	if (threadIdx.x < NR) { S.reset[threadIdx.x] = mirror<T>((T)D->reset[threadIdx.x]); S.start[threadIdx.x] = mirror<T>((T)D->start[threadIdx.x]); }
 	if (threadIdx.x < 2 * AGB_MAXDELIM + 2) S.delim[threadIdx.x] = D->delim[threadIdx.x];
 	if (threadIdx.x <= AGB_MAXERR) S.hist[threadIdx.x] = 0;
-	C.init1 = (T)D->init1; C.noerr = (T)D->noerr; C.endpos = (T)D->endpos; C.dendpos = (T)D->dendpos;
+	C.init1 = mirror<T>((T)D->init1); C.noerr = mirror<T>((T)D->noerr); C.endpos = mirror<T>((T)D->endpos); C.dendpos = mirror<T>((T)D->dendpos);
 	C.L = D->L; C.k = D->k; C.and_mode = D->and_mode; C.inverse = D->inverse; C.kind = D->delim_kind;
 	C.ci = D->cost_i; C.cs = D->cost_s; C.cd = D->cost_d;
 	__syncthreads();
@@ -266,21 +282,21 @@ __device__ __forceinline__ void rows_step(T (&S)[NR], T cm, const DevConsts<T> &
 {
 	if (!COSTS) {
 		T prevB = S[0];
-		T prevA = ((prevB >> 1) & cm) | (C.init1 & prevB);
+		T prevA = (shift1<T>(prevB) & cm) | (C.init1 & prevB);
 #pragma unroll
 		for (int r = 1; r < NR; r++) {
 			T b = S[r];
-			T a = ((b >> 1) & cm) | (C.init1 & b) | prevB | (((prevA | prevB) >> 1) & C.noerr);
+			T a = (shift1<T>(b) & cm) | (C.init1 & b) | prevB | (shift1<T>(prevA | prevB) & C.noerr);
 			S[r - 1] = prevA; prevA = a; prevB = b;
 		}
 		S[NR - 1] = prevA;
 	} else {
 		T A[NR];
-		A[0] = ((S[0] >> 1) & cm) | (C.init1 & S[0]);
+		A[0] = (shift1<T>(S[0]) & cm) | (C.init1 & S[0]);
 #pragma unroll
 		for (int r = 1; r < NR; r++) {
 			T bi = (r - C.ci >= 0) ? S[r - C.ci] : (T)0, ad = (r - C.cd >= 0) ? A[r - C.cd] : (T)0, bs = (r - C.cs >= 0) ? S[r - C.cs] : (T)0;
-			A[r] = ((S[r] >> 1) & cm) | bi | (((ad | bs) >> 1) & C.noerr) | (C.init1 & S[r]);
+			A[r] = (shift1<T>(S[r]) & cm) | bi | (shift1<T>(ad | bs) & C.noerr) | (C.init1 & S[r]);
 		}
 #pragma unroll
 		for (int r = 0; r < NR; r++) S[r] = A[r];
@@ -334,38 +350,6 @@ __device__ __forceinline__ bool window_passes(const uint8_t *bytes, const bool r
 		rows_step<T, NR, COSTS>(S, mask[c], C);
 	}
 	return run && (S[NR - 1] & C.endpos) != 0;
-}
-
-/* The same walk on the bit-reversed automaton (32-bit rows, unit costs): every word -- masks, Init0/1, NO_ERR,
- * endposition -- is mirrored with __brev once, which turns the recurrence's `>> 1` into `<< 1`.  A left shift by
- * one is a multiply by two, and IMAD runs on the FMA pipe, which this kernel leaves idle, instead of the ALU pipe
- * that bounds it: 5 ALU + 2 FMA operations per row and byte instead of 7 ALU. */
-__device__ __forceinline__ uint32_t shl1_fma(uint32_t x)
-{
-	uint32_t r;
-	asm("mad.lo.u32 %0, %1, 2, 0;" : "=r"(r) : "r"(x));
-	return r;
-}
-template <int NR>
-__device__ __forceinline__ bool window_passes_mirror(const uint8_t *bytes, const bool run, const int wlen, const uint32_t init0,
-                                                     const uint32_t *mask, const uint32_t init1, const uint32_t noerr, const uint32_t endpos)
-{
-	uint32_t S[NR];
-#pragma unroll
-	for (int r = 0; r < NR; r++) S[r] = init0;
-	for (int q = 0; q < wlen; q++) {
-		const uint32_t cm = mask[run ? bytes[q] : 0];
-		uint32_t prevB = S[0];
-		uint32_t prevA = (shl1_fma(prevB) & cm) | (init1 & prevB);
-#pragma unroll
-		for (int r = 1; r < NR; r++) {
-			const uint32_t b = S[r];
-			const uint32_t a = (shl1_fma(b) & cm) | (init1 & b) | prevB | (shl1_fma(prevA | prevB) & noerr);
-			S[r - 1] = prevA; prevA = a; prevB = b;
-		}
-		S[NR - 1] = prevA;
-	}
-	return run && (S[NR - 1] & endpos) != 0;
 }
 
 /* which of the 16 windows of a chunk start an anchor: bit (32 + s - off_a) per hit, i.e. the distinct WINDOW STARTS
@@ -477,20 +461,13 @@ template <typename T, int NR, bool COSTS, int NGC>
 __global__ void __launch_bounds__(REFINE_THREADS)
 k_refine(const RefineParams P)
 {
-	constexpr bool MIRROR = (sizeof(T) == 4) && !COSTS;     /* window_passes_mirror() */
 	extern __shared__ __align__(16) uint32_t s_stage[];     /* REFINE_THREADS x (ng*4 + 1) words */
 	__shared__ RecShared<T, NR> SH;
 	__shared__ uint32_t s_ring[REFINE_THREADS / 32][REFINE_RING];
 	__shared__ unsigned long long s_defer[REFINE_THREADS / 32][REFINE_DEFER];
 	DevConsts<T> C;
 	shared_init<T, NR>(SH, C, P.desc, REFINE_THREADS);
-	const T init0 = (T)P.desc->init0;
-	uint32_t m_init0 = 0, m_init1 = 0, m_noerr = 0, m_endpos = 0;
-	if (MIRROR) {
-		for (int i = threadIdx.x; i < 257; i += REFINE_THREADS) SH.mask[i] = (T)__brev((uint32_t)SH.mask[i]);
-		m_init0 = __brev((uint32_t)init0); m_init1 = __brev((uint32_t)C.init1); m_noerr = __brev((uint32_t)C.noerr); m_endpos = __brev((uint32_t)C.endpos);
-		__syncthreads();
-	}
+	const T init0 = mirror<T>((T)P.desc->init0);
 	const int pat_len = P.desc->pat_len, k = C.k, wlen = pat_len + 2 * k;
 	const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5, lt_mask = (1u << lane) - 1u;
 	const int stride_w = P.ng * 4 + 1;                      /* odd number of words: lanes hit different banks */
@@ -499,8 +476,7 @@ k_refine(const RefineParams P)
 	const int ws0 = P.gb * 16 - 32 - k;                     /* window offset in the staged bytes = ws0 + start bit */
 	uint32_t *ring = s_ring[wib];
 	unsigned long long *defer = s_defer[wib];
-#define REFINE_WINDOW(ptr, run) (MIRROR ? window_passes_mirror<NR>((ptr), (run), wlen, m_init0, reinterpret_cast<const uint32_t *>(SH.mask), m_init1, m_noerr, m_endpos) \
-                                        : window_passes<T, NR, COSTS>((ptr), (run), wlen, init0, SH.mask, C))
+#define REFINE_WINDOW(ptr, run) window_passes<T, NR, COSTS>((ptr), (run), wlen, init0, SH.mask, C)
 
 	/* this warp's groups of 32 bitmap words: [g_begin, g_end) */
 	const uint64_t warp = ((uint64_t)blockIdx.x * REFINE_THREADS + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * REFINE_THREADS) >> 5;
