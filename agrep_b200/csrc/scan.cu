@@ -108,7 +108,10 @@ __device__ __forceinline__ uint32_t windows_test(uint32_t lo, uint32_t hi, const
 		uint32_t f[4];
 #pragma unroll
 		for (int t = 0; t < 4; t++) {
-			uint32_t r = w[t] * P.one + P.coef[NA - 1];
+			/* Horner.  IMAD (FMA pipe, 64 lanes/clk/SM) and the ALU pipe (64 lanes/clk/SM) both count: with three
+			 * or more anchors the first step, w + c, goes to the ALU pipe as VIADDMNMX (min(w + c, ~0)), which
+			 * leaves NA-1 IMADs per window; `one` is a runtime 1 that keeps the step an IMAD otherwise */
+			uint32_t r = (NA >= 3) ? __viaddmin_u32(w[t], P.coef[NA - 1], 0xFFFFFFFFu) : w[t] * P.one + P.coef[NA - 1];
 #pragma unroll
 			for (int i = NA - 2; i >= 0; i--) r = r * w[t] + P.coef[i];
 			f[t] = MASKED ? r * P.scale : r;
