@@ -130,6 +130,36 @@ __device__ __forceinline__ uint32_t windows_test(uint32_t lo, uint32_t hi, const
 	return acc;
 }
 
+/* the FRONT_CH chunks a thread takes from one stage; FULL = no chunk of the stage is near the end of the text */
+template <int NA, bool MASKED, bool FOLD, bool POLY, bool FULL>
+__device__ __forceinline__ void front_chunks(const FrontParams &P, const uint8_t *st, uint32_t tid, uint32_t lane, uint32_t rem, uint32_t *bm)
+{
+#pragma unroll
+	for (int c = 0; c < FRONT_CH; c++) {
+		const uint32_t idx = c * FRONT_THREADS + tid;
+		uint4 v = *reinterpret_cast<const uint4 *>(st + idx * 16);
+		/* the first word of the next chunk (a 4-way bank conflict, measured cheaper than SHFL + a predicated LDS:
+		 * 4905 vs 4787 GB/s, profiles/round1_front_variants.md) */
+		uint32_t x4 = *reinterpret_cast<const uint32_t *>(st + idx * 16 + 16);
+		if (FOLD) { v.x |= P.fold; v.y |= P.fold; v.z |= P.fold; v.w |= P.fold; x4 |= P.fold; }
+		uint32_t acc = 0xffffffffu;
+		acc = windows_test<NA, MASKED, POLY>(v.x, v.y, P, acc);
+		acc = windows_test<NA, MASKED, POLY>(v.y, v.z, P, acc);
+		acc = windows_test<NA, MASKED, POLY>(v.z, v.w, P, acc);
+		acc = windows_test<NA, MASKED, POLY>(v.w, x4, P, acc);
+		if (FULL) {
+			const uint32_t word = __ballot_sync(0xffffffffu, acc == 0);
+			if (lane == 0) bm[c * (FRONT_THREADS / 32)] = word;
+		} else {
+			/* the last chunks are always passed on: a match may run into the delimiter appended at EOF
+			 * (bitap.c:161-165), and their look-ahead bytes may not exist */
+			const bool flag = (idx < rem) && (acc == 0 || idx + 2 >= rem);
+			const uint32_t word = __ballot_sync(0xffffffffu, flag);
+			if (lane == 0 && idx < rem) bm[c * (FRONT_THREADS / 32)] = word;
+		}
+	}
+}
+
 /* Persistent CTAs.  Thread 0 keeps FRONT_NST bulk copies of 16 KiB (+16 B) in flight into a shared-memory
  * ring, each completing on its own mbarrier; all 256 threads take 4 chunks per stage from shared memory
  * (LDS.128, conflict-free: a warp reads 512 consecutive bytes), test the 16 windows of each chunk and ballot
@@ -169,30 +199,8 @@ k_front(const FrontParams P)
 		uint32_t *bm = P.bitmap + sg * FRONT_WORDS_PER_STAGE + warp_in_cta;
 		/* full = every chunk of the stage exists and none is among the last two of the text: no per-chunk EOF logic */
 		const bool full = left >= FRONT_STAGE_CHUNKS + 2;
-#pragma unroll
-		for (int c = 0; c < FRONT_CH; c++) {
-			const uint32_t idx = c * FRONT_THREADS + tid;
-			uint4 v = *reinterpret_cast<const uint4 *>(st + idx * 16);
-			/* the first word of the next chunk (a 4-way bank conflict, measured cheaper than SHFL + a predicated LDS:
-			 * 4905 vs 4787 GB/s, profiles/round1_front_variants.md) */
-			uint32_t x4 = *reinterpret_cast<const uint32_t *>(st + idx * 16 + 16);
-			if (FOLD) { v.x |= P.fold; v.y |= P.fold; v.z |= P.fold; v.w |= P.fold; x4 |= P.fold; }
-			uint32_t acc = 0xffffffffu;
-			acc = windows_test<NA, MASKED, POLY>(v.x, v.y, P, acc);
-			acc = windows_test<NA, MASKED, POLY>(v.y, v.z, P, acc);
-			acc = windows_test<NA, MASKED, POLY>(v.z, v.w, P, acc);
-			acc = windows_test<NA, MASKED, POLY>(v.w, x4, P, acc);
-			if (full) {
-				const uint32_t word = __ballot_sync(0xffffffffu, acc == 0);
-				if (lane == 0) bm[c * (FRONT_THREADS / 32)] = word;
-			} else {
-				/* the last chunks are always passed on: a match may run into the delimiter appended at EOF
-				 * (bitap.c:161-165), and their look-ahead bytes may not exist */
-				const bool flag = (idx < rem) && (acc == 0 || idx + 2 >= rem);
-				const uint32_t word = __ballot_sync(0xffffffffu, flag);
-				if (lane == 0 && idx < rem) bm[c * (FRONT_THREADS / 32)] = word;
-			}
-		}
+		if (full) front_chunks<NA, MASKED, FOLD, POLY, true>(P, st, tid, lane, rem, bm);
+		else front_chunks<NA, MASKED, FOLD, POLY, false>(P, st, tid, lane, rem, bm);
 		__syncthreads();                       /* everyone is done reading this slot */
 		if (tid == 0) issue((uint64_t)it + FRONT_NST);   /* refill it with the stage FRONT_NST iterations ahead */
 	}
