@@ -1080,39 +1080,47 @@ k_records_slices(const RecParams P)
 			_Pragma("unroll") for (int r = 0; r < NR; r++) S[r] = RS[r]; \
 		} while (0)
 
-		if (easy && !P.levels && !writing) {
-			/* plain counting away from both ends of the text: every record counts (agrep.c:3811 only bites at the ends),
-			 * so a close is a verdict, an add and the reset -- short enough to be predicated rather than branched around */
-			/* The close is written with selects: a branch here is taken by one or two lanes in almost every other step
-			 * of a warp (a line ends every ~60 bytes), and the divergence and reconvergence cost far more latency
-			 * than the dozen predicated instructions (measured: 260 cycles per step and warp with the branch).
-			 * match test (bitap.c:182) folded to one compare: ok = ((row & e) == cmp) != flip */
-			const T e_ = (C.and_mode && C.inverse) ? (T)0 : C.endpos;
-			const T cmp_ = (C.and_mode && !C.inverse) ? C.endpos : (T)0;
-			const bool flip_ = !C.and_mode && !C.inverse;
-			int first_j = -1, last_j = -1; T fb = 0;
+		if (easy && !P.levels && !writing && !C.and_mode) {
+			/* Plain counting away from both ends of the text: every record counts (agrep.c:3811 only bites at the ends).
+			 * No branch on a close: one would be taken by one or two lanes in almost every other step of a warp (a line
+			 * ends every ~60 bytes) and the divergence costs far more than it skips (measured: 260 cycles per step and
+			 * warp).  The loop only resets the rows with selects and shifts two flags per step into a pair of 32-bit
+			 * histories -- "a record closed here", "and an end bit was up" (bitap.c:182 without -v; `;` patterns take
+			 * the general loop) -- which are counted and located with popc/clz/ffs once per 32 bytes. */
+			int first_j = -1, last_j = -1; bool first_found = false;
+			const bool inv = C.inverse != 0;
 			uint32_t w = *reinterpret_cast<const uint32_t *>(mine);
-			for (uint32_t j = 0; j < SL_PER; j += 4) {                  /* easy: the whole slice is text */
-				const uint32_t wn = *reinterpret_cast<const uint32_t *>(mine + j + 4);   /* (the last one reads the strip's padding) */
-				T m[4];
+			for (uint32_t jb = 0; jb < SL_PER; jb += 32) {              /* easy: the whole slice is text */
+				uint32_t cw = 0, fw = 0;                                   /* step jb + s  <->  bit 31 - s */
+#pragma unroll (NR <= 3 ? 8 : 1)                                    /* many rows: the body is long enough, keep it in the instruction cache */
+				for (int g = 0; g < 8; g++) {
+					const uint32_t wn = *reinterpret_cast<const uint32_t *>(mine + jb + 4 * g + 4);   /* (the last one reads the strip's padding) */
+					T m[4];
 #pragma unroll
-				for (int i = 0; i < 4; i++) m[i] = SH.mask[(w >> (8 * i)) & 0xFFu];
+					for (int i = 0; i < 4; i++) m[i] = SH.mask[(w >> (8 * i)) & 0xFFu];
 #pragma unroll
-				for (int i = 0; i < 4; i++) {
-					rows_step<T, NR, COSTS>(S, m[i], C);
-					const T last = S[NR - 1];
-					const bool cl = (S[0] & C.dendpos) != 0;
-					const bool firstc = cl && last_j < 0;                  /* the record it ends opened before my slice */
-					const bool ok = ((last & e_) == cmp_) != flip_;
-					fb = firstc ? (T)(last & C.endpos) : fb;
-					first_j = firstc ? (int)(j + i) : first_j;
-					cnt += (cl && !firstc && ok) ? 1u : 0u;
-					last_j = cl ? (int)(j + i) : last_j;
+					for (int i = 0; i < 4; i++) {
+						rows_step<T, NR, COSTS>(S, m[i], C);
+						const bool cl = (S[0] & C.dendpos) != 0;
+						cw = cw * 2u + (cl ? 1u : 0u);
+						fw = fw * 2u + ((S[NR - 1] & C.endpos) ? 1u : 0u);         /* sticky: only looked at where cw has a bit */
 #pragma unroll
-					for (int r = 0; r < NR; r++) S[r] = cl ? RS[r] : S[r];
+						for (int r = 0; r < NR; r++) S[r] = cl ? RS[r] : S[r];
+					}
+					w = wn;
 				}
-				w = wn;
+				if (cw) {
+					uint32_t hits = cw & (inv ? ~fw : fw);
+					if (last_j < 0) {                                        /* the slice's first close: that record opened before my slice */
+						const int sft = __clz(cw);
+						first_j = (int)jb + sft; first_found = ((fw >> (31 - sft)) & 1u) != 0;
+						hits &= ~(0x80000000u >> sft);
+					}
+					cnt += __popc(hits);
+					last_j = (int)jb + 32 - __ffs(cw);
+				}
 			}
+			const T fb = first_found ? C.endpos : (T)0;
 			if (first_j >= 0 && pass == 0) { has_first = true; first_end = a + first_j + 1 - L; first_bits[NR - 1] = fb; }
 			if (last_j >= 0) { begin = a + last_j + 1 - L; have_begin = true; }
 		} else {

@@ -86,6 +86,37 @@ def test_long_records_and_no_delimiter():
         check("a[bc]d", data, k=0, linenum=1)       # no anchors: every chunk goes to the record stage
 
 
+def test_dense_forms_on_ragged_records():
+    """no anchor plan (classes, -v, tiny patterns, `;`): the record stage walks every byte -- the slices form (fixed
+    256-byte slices per thread, records spanning slices and 32 KiB tiles resolved afterwards) or, for '#', -p and
+    run delimiters, the dense tile form.  Records of every awkward length: empty, 1, around the slice size, longer
+    than a tile."""
+    rnd = random.Random(11)
+    words = [w for w in TEXT.decode().split() if w.isalpha()]
+    lines = []
+    for i in range(2500):
+        ln = rnd.choice([0, 0, 1, 2, 5, 30, 60, 90, 255, 256, 257, 300, 511, 513, 1000, 4000])
+        if i in (700, 1900): ln = 40000 + i
+        row = ""
+        while len(row) < ln: row += rnd.choice(words) + " "
+        lines.append(row[:ln])
+    data = "\n".join(lines).encode()
+    for tail in (b"", b"\n", b"\n\n"):
+        d = data + tail
+        check("t[hx]e", d, k=0, linenum=1)
+        check("th", d, k=1, linenum=1)
+        check("because", d, k=2, linenum=1, inverse=1)
+        check("people;state", d, k=1, linenum=1)
+        check("gover#ent", d, k=1, linenum=1)
+        check("wh[aeiou]ch", d, k=1, linenum=1, delim="e ")
+        check("governmental", d, k=8, linenum=1)
+    a = _oracle.compile("t[hx]ese", k=3, linenum=1)
+    cnt, hist, recs = _oracle.scan_levels(a, 3, data)
+    res, got = ag.Pattern("t[hx]ese", k=3, linenum=1).scan_host(data, levels=True)
+    assert res.n_matched == cnt and list(res.level_hist)[:4] == hist[:4]
+    assert [(b, e, l) for b, e, _, l in got] == [(b, e, l) for b, e, _, l in recs]
+
+
 def test_wide_pattern_64bit_rows():
     pat = "people how too little state good very make"      # 42 chars -> M = 44
     data = TEXT + b"xx people how too little state good very make yy\nxx people hxw too litle state good very make\n"
