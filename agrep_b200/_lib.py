@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libagrepb200.so")
 
 AGB_MAXERR, AGB_MAXDELIM, AGB_MAXANCHOR = 8, 8, 24
-WANT_COUNT, WANT_RECORDS, WANT_LEVELS = 0, 1, 4
+WANT_COUNT, WANT_RECORDS, WANT_ORDINALS, WANT_LEVELS = 0, 1, 2, 4
 PLAN_ALL, PLAN_ANCHORS = 0, 1
 ENGINE_NAMES = {0: "bitap", 1: "asearch", 2: "asearch0", 3: "asearch1", 4: "sgrep_bm"}
 
@@ -41,7 +41,8 @@ class Record(C.Structure):
 
 class Result(C.Structure):
     _fields_ = [("n_matched", C.c_uint64), ("n_records", C.c_uint64), ("n_flagged", C.c_uint64),
-                ("level_hist", C.c_uint64 * (AGB_MAXERR + 1)), ("ms_front", C.c_float), ("ms_records", C.c_float)]
+                ("level_hist", C.c_uint64 * (AGB_MAXERR + 1)), ("ms_front", C.c_float), ("ms_records", C.c_float),
+                ("n_closes", C.c_uint64)]
 
 
 class CorpusSpec(C.Structure):

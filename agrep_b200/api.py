@@ -6,7 +6,7 @@ switches by name; `scan_*` return what exec() derives from the scan functions: n
 (lasti, print_end, j) triples handed to output() (agrep.c:3805).  All work happens in libagrepb200.so."""
 import ctypes as C
 from . import _lib
-from ._lib import (Options, Desc, Record, Result, CorpusSpec, WANT_COUNT, WANT_RECORDS, WANT_LEVELS,
+from ._lib import (Options, Desc, Record, Result, CorpusSpec, WANT_COUNT, WANT_RECORDS, WANT_ORDINALS, WANT_LEVELS,
                    PLAN_ALL, PLAN_ANCHORS, ENGINE_NAMES)
 
 
@@ -52,10 +52,11 @@ class Pattern:
         out = [(recs[i].begin, recs[i].end, recs[i].ordinal, recs[i].level) for i in range(res.n_records)] if recs is not None else []
         return res, out
 
-    def scan_host(self, data, want_records=True, capacity=None, levels=False):
-        """data: bytes-like in host memory (the fill_buf path: H2D inside the call)."""
+    def scan_host(self, data, want_records=True, capacity=None, levels=False, ordinals=False):
+        """data: bytes-like in host memory (the fill_buf path: H2D inside the call).
+        ordinals: also fill Record.ordinal (the j that -n prints) and Result.n_closes on the device."""
         n = len(data)
-        want = (WANT_RECORDS if want_records else WANT_COUNT) | (WANT_LEVELS if levels else 0)
+        want = (WANT_RECORDS if want_records else WANT_COUNT) | (WANT_LEVELS if levels else 0) | (WANT_ORDINALS if ordinals else 0)
         cap = (capacity if capacity is not None else n // 2 + 16) if want_records else 0
         recs = (Record * cap)() if cap else None
         res = Result()
@@ -63,9 +64,9 @@ class Pattern:
         rc = _lib.lib().agb_scan_host(self._h, buf, n, want, recs, cap, C.byref(res))
         return self._finish(rc, res, recs, want)
 
-    def scan_device(self, dev_ptr, n, stream=0, d_records=0, capacity=0, levels=False):
+    def scan_device(self, dev_ptr, n, stream=0, d_records=0, capacity=0, levels=False, ordinals=False):
         """dev_ptr: device address of n bytes (16-byte aligned, e.g. torch tensor .data_ptr())."""
-        want = (WANT_RECORDS if capacity else WANT_COUNT) | (WANT_LEVELS if levels else 0)
+        want = (WANT_RECORDS if capacity else WANT_COUNT) | (WANT_LEVELS if levels else 0) | (WANT_ORDINALS if ordinals else 0)
         res = Result()
         rc = _lib.lib().agb_scan_device(self._h, C.c_void_p(dev_ptr), n, want, C.c_void_p(d_records), capacity,
                                         C.c_void_p(stream), C.byref(res))

@@ -76,12 +76,11 @@ static int scan_files(const agb_pattern *p, char **files, int nfiles, int counti
 		if (!hb) continue;
 		cap = count_only ? 0 : n / 2 + 16;
 		if (cap) recs = (agb_record *)malloc(cap * sizeof *recs);
-		rc = agb_scan_host(p, hb + 1, n, count_only ? AGB_WANT_COUNT : AGB_WANT_RECORDS, recs, cap, &res);
+		rc = agb_scan_host(p, hb + 1, n, count_only ? AGB_WANT_COUNT : (AGB_WANT_RECORDS | AGB_WANT_ORDINALS)   /* output() needs j even without -n (agrep.c:3815) */, recs, cap, &res);
 		if (rc) { fprintf(stderr, "%s: scan failed: %s\n", prog, agb_last_error()); exit(255); }   /* no CPU fallback */
 		if (FILENAMEONLY && !counting) num_of_matched += res.n_matched ? 1 : 0;   /* the scan stops at the first hit (bitap.c:184-210, sgrep.c:813-814) */
 		else if (count_only) num_of_matched += (int)res.n_matched;
 		else {
-			agb_fill_ordinals(p, hb + 1, n, recs, res.n_records);
 			for (i = 0; i < res.n_records; i++) print_record(hb, d, &recs[i], fname ? fname : "");
 		}
 		if (!counting) {

@@ -180,9 +180,8 @@ static int scan_and_replay(char old_D_pat[], const unsigned char *Pattern, int f
 	cap = n / 2 + 16;                                       /* a record is at least one byte + delimiter */
 	recs = (agb_record *)malloc(cap * sizeof *recs);
 	if (!recs) { ret = -1; errno = AGREP_ERROR; goto done; }
-	rc = agb_scan_host(p, hb + 1, n, AGB_WANT_RECORDS, recs, cap, &res);
+	rc = agb_scan_host(p, hb + 1, n, AGB_WANT_RECORDS | (LINENUM ? AGB_WANT_ORDINALS : 0), recs, cap, &res);   /* j for output() (-n) on the device */
 	if (rc) { ret = fail("scan"); goto done; }
-	if (LINENUM && res.n_records) agb_fill_ordinals(p, hb + 1, n, recs, res.n_records);   /* j for output() (-n) */
 	for (i = 0; i < res.n_records; i++) {
 		if (fd == -1 && recs[i].end >= (long long)n) continue;      /* memory mode appends no delimiter (bitap.c:310-314) */
 		if (FILENAMEONLY && (NEW_FILE || !POST_FILTER)) {       /* bitap.c:184-210 */

@@ -1441,11 +1441,113 @@ extern "C" int agb_corpus_fill_host(const agb_corpus_spec *s, void *h_text)
 #define H2D_SLICE   (64ull << 20)      /* bytes per H2D slice of agb_scan_host; a multiple of the 16 KiB stage */
 #define STAGE_BUFS  3
 
+/* ================================================================================================
+ * ordinals: j of the reference's loops (bitap.c:178, asearch.c:120), what -n prints minus one.
+ *
+ * j is incremented at every record close, the virtual '\n' included, so the ordinal of a record is the number of
+ * delimiter ends at or before the delimiter that closes it -- a property of the text alone.  k_delim_count counts
+ * the delimiter ends of every 512-byte block (16-bit) and every 32 KiB tile (one more HBM-bound pass, only when
+ * ordinals are asked for); the tile counts are scanned; k_ordinals gives every record tile prefix + the blocks
+ * of its tile before its own + the delimiter ends of its own block up to its close.  Same delimiter rule as
+ * delim_ends_at() / agb_fill_ordinals(): every occurrence of a border-free delimiter, greedy pairing from the
+ * start of the run for c^L ("$$"), the virtual '\n' and the delimiter appended at EOF included.
+ * ============================================================================================== */
+#define ORD_THREADS 256
+#define ORD_TILE    32768
+#define ORD_PER     (ORD_TILE / ORD_THREADS)       /* 128 bytes per thread */
+#define ORD_BLOCK   512
+
+struct OrdParams {
+	const uint8_t *text; uint64_t n;
+	uint16_t *blocks; uint32_t *tiles; const uint64_t *tile_off;
+	agb_record *records; const unsigned long long *totals; uint64_t capacity;
+	uint8_t delim[AGB_MAXDELIM + 2]; int L, kind;
+	long long j0;                /* 0, or -1 when the text starts with the user's delimiter (bitap.c:151-156) */
+};
+
+/* delimiter ends in [from, to) (file offsets; to <= n + L), sequentially; run: the length of the run of delim[0]
+ * that ends at from - 1 (kind 1) */
+__device__ __forceinline__ uint32_t ord_count_seq(Reader &R, const OrdParams &P, int64_t from, int64_t to)
+{
+	uint32_t cnt = 0;
+	if (P.L == 1) { for (int64_t q = from; q < to; q++) cnt += R.get(q) == P.delim[0]; return cnt; }
+	if (P.kind == 0) {
+		for (int64_t q = from; q < to; q++) {
+			bool m = true;
+			for (int u = 0; u < P.L && m; u++) m = R.get(q - u) == P.delim[P.L - 1 - u];
+			cnt += m ? 1u : 0u;
+		}
+		return cnt;
+	}
+	const int c = P.delim[0];
+	int64_t run = 0;
+	for (int64_t q = from - 1; q >= -1 && R.get(q) == c; q--) run++;       /* (-1 is the virtual '\n') */
+	for (int64_t q = from; q < to; q++) {
+		run = R.get(q) == c ? run + 1 : 0;
+		cnt += (run > 0 && run % P.L == 0) ? 1u : 0u;
+	}
+	return cnt;
+}
+
+__global__ void __launch_bounds__(ORD_THREADS) k_delim_count(const OrdParams P)
+{
+	__shared__ uint32_t s_warp[ORD_THREADS / 32];
+	const uint32_t tid = threadIdx.x, lane = tid & 31;
+	const int64_t n = (int64_t)P.n, limit = n + P.L;
+	const int64_t s0 = (int64_t)blockIdx.x * ORD_TILE + (int64_t)tid * ORD_PER, s1 = s0 + ORD_PER < limit ? s0 + ORD_PER : limit;
+	uint32_t cnt = 0;
+	if (s0 < limit) {
+		if (P.L == 1 && s0 + ORD_PER <= n) {
+			/* 16 bytes at a time: exact per-byte equality by SWAR (0x80 where the byte equals the delimiter) */
+			const uint32_t d4 = P.delim[0] * 0x01010101u;
+#pragma unroll
+			for (int v = 0; v < ORD_PER / 16; v++) {
+				const uint4 x = __ldg(reinterpret_cast<const uint4 *>(P.text + s0) + v);
+				const uint32_t xs[4] = { x.x, x.y, x.z, x.w };
+#pragma unroll
+				for (int w = 0; w < 4; w++) {
+					const uint32_t t = xs[w] ^ d4;
+					cnt += __popc(~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t | 0x7F7F7F7Fu));
+				}
+			}
+		} else {
+			Reader R; R.init(P.text, P.n, P.delim, P.L);
+			cnt = ord_count_seq(R, P, s0, s1);
+		}
+	}
+	/* 4 threads = one 512-byte block; 256 threads = the tile */
+	uint32_t b = cnt;
+	b += __shfl_xor_sync(0xffffffffu, b, 1); b += __shfl_xor_sync(0xffffffffu, b, 2);
+	if ((tid & 3) == 0) P.blocks[(uint64_t)blockIdx.x * (ORD_TILE / ORD_BLOCK) + (tid >> 2)] = (uint16_t)b;
+	uint32_t w = __reduce_add_sync(0xffffffffu, cnt);
+	if (lane == 0) s_warp[tid >> 5] = w;
+	__syncthreads();
+	if (tid == 0) { uint32_t t = 0; for (int i = 0; i < ORD_THREADS / 32; i++) t += s_warp[i]; P.tiles[blockIdx.x] = t; }
+}
+
+__global__ void __launch_bounds__(256) k_ordinals(const OrdParams P)
+{
+	unsigned long long nrec = P.totals[0];
+	if (nrec > P.capacity) nrec = P.capacity;
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nrec) return;
+	const int64_t q = P.records[i].end + P.L - 1;                          /* the last byte of the closing delimiter */
+	const uint64_t tile = (uint64_t)q / ORD_TILE, blk = (uint64_t)q / ORD_BLOCK;
+	unsigned long long j = P.tile_off[tile];
+	for (uint64_t b = tile * (ORD_TILE / ORD_BLOCK); b < blk; b++) j += P.blocks[b];
+	Reader R; R.init(P.text, P.n, P.delim, P.L);
+	j += ord_count_seq(R, P, (int64_t)(blk * ORD_BLOCK), q + 1);
+	/* the virtual '\n' closes a record of its own when it completes a delimiter: only a 1-byte '\n' can */
+	const long long virt = (P.L == 1 && P.delim[0] == '\n') ? 1 : 0;
+	P.records[i].ordinal = (long long)j + virt + P.j0;
+}
+
 struct Workspace {               /* grow-only device scratch, one per device */
 	uint32_t *bitmap = nullptr; size_t bitmap_bytes = 0;
 	uint32_t *tile_counts = nullptr; uint64_t *tile_offsets = nullptr; size_t tiles = 0;
 	uint64_t *cand = nullptr; uint32_t *cand_counts = nullptr; uint64_t *cand_offsets = nullptr; agb_record *cand_first = nullptr; size_t cand_cap = 0;
 	uint32_t *scan_sums = nullptr; uint64_t *scan_offs = nullptr; size_t scan_cap = 0;
+	uint16_t *ord_blocks = nullptr; size_t ord_blocks_cap = 0;     /* delimiter ends per 512-byte block (AGB_WANT_ORDINALS) */
 	unsigned long long *totals = nullptr;          /* 16 counters */
 	unsigned long long *h_totals = nullptr;        /* pinned */
 	agb_desc *d_desc = nullptr; agb_desc h_desc_copy; bool desc_valid = false;
@@ -1880,6 +1982,45 @@ static int records_launch(const agb_desc &d, Workspace &W, const void *d_text, u
 	return AGB_OK;
 }
 
+/* AGB_WANT_ORDINALS: fill agb_record.ordinal of the list just written and leave the number of record closes of the
+ * whole text (j after the last record, the basis of the next shard's ordinals) in totals[13].  Runs after the
+ * record stage, whose tile scratch it reuses. */
+static int ordinals_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, agb_record *d_records,
+                           uint64_t capacity, cudaStream_t st)
+{
+	uint8_t *h_head = reinterpret_cast<uint8_t *>(W.h_totals + 14);      /* pinned scratch: the first bytes of the text */
+	if (n >= (uint64_t)d.L && d.user_delim) {
+		CUDA_TRY(cudaMemcpyAsync(h_head, d_text, (size_t)d.L, cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+	}
+	const uint64_t limit = n + (uint64_t)d.L, tiles = (limit + ORD_TILE - 1) / ORD_TILE;
+	if (tiles + 1 > W.tiles) return AGB_ERR_NOMEM;                       /* (ws_prepare sized them for n + one tile) */
+	const size_t nb = (size_t)tiles * (ORD_TILE / ORD_BLOCK);
+	if (nb > W.ord_blocks_cap) {
+		if (W.ord_blocks) cudaFree(W.ord_blocks);
+		W.ord_blocks = nullptr; W.ord_blocks_cap = 0;
+		CUDA_TRY(cudaMalloc(&W.ord_blocks, nb * sizeof(uint16_t))); W.ord_blocks_cap = nb;
+	}
+	OrdParams P; memset(&P, 0, sizeof P);
+	P.text = (const uint8_t *)d_text; P.n = n; P.blocks = W.ord_blocks; P.tiles = W.tile_counts; P.tile_off = W.tile_offsets;
+	P.records = d_records; P.totals = W.totals; P.capacity = capacity;
+	memcpy(P.delim, d.delim, AGB_MAXDELIM + 2 < sizeof d.delim ? AGB_MAXDELIM + 2 : sizeof d.delim);
+	P.L = d.L; P.kind = d.delim_kind;
+	/* bitap.c:151-156: j starts at -1 when the text begins with the user's delimiter (asearch0() has no such correction) */
+	P.j0 = (d.user_delim && d.engine != AGB_ENGINE_ASEARCH0 && n >= (uint64_t)d.L && memcmp(h_head, d.delim, (size_t)d.L) == 0) ? -1 : 0;
+	k_delim_count<<<(unsigned)tiles, ORD_THREADS, 0, st>>>(P); g_launches++;
+	k_scan_tiles<<<1, 1024, 0, st>>>(W.tile_counts, W.tile_offsets, tiles, W.totals + 13); g_launches++;
+	if (d_records && capacity) {
+		/* the list length is on the device (totals[0]); one thread per possible entry, bounded by the capacity */
+		CUDA_TRY(cudaMemcpyAsync(W.h_totals, W.totals, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+		const uint64_t nrec = std::min<uint64_t>(W.h_totals[0], capacity);
+		if (nrec) { k_ordinals<<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(P); g_launches++; }
+	}
+	CUDA_TRY(cudaGetLastError());
+	return AGB_OK;
+}
+
 static int fetch_result(Workspace &W, int want, uint64_t capacity, cudaStream_t st, agb_result *res)
 {
 	CUDA_TRY(cudaMemcpyAsync(W.h_totals, W.totals, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -1888,6 +2029,7 @@ static int fetch_result(Workspace &W, int want, uint64_t capacity, cudaStream_t 
 	res->n_flagged = W.h_totals[1];
 	for (int i = 0; i <= AGB_MAXERR; i++) res->level_hist[i] = W.h_totals[2 + i];
 	res->n_records = (want & AGB_WANT_RECORDS) ? std::min<uint64_t>(res->n_matched, capacity) : 0;
+	res->n_closes = (want & AGB_WANT_ORDINALS) ? W.h_totals[13] : 0;
 	return AGB_OK;
 }
 
@@ -1911,6 +2053,7 @@ static int scan_device_impl(const agb_desc &d, const void *d_text, uint64_t n, i
 	CUDA_TRY(cudaEventRecord(W.e1, st));
 	if (use_front) { rc = refine_launch(d, W, d_text, n, st); if (rc) return rc; }
 	rc = records_launch(d, W, d_text, n, use_front, want, want_level, d_records, capacity, st); if (rc) return rc;
+	if (want & AGB_WANT_ORDINALS) { rc = ordinals_launch(d, W, d_text, n, (want & AGB_WANT_RECORDS) ? d_records : nullptr, capacity, st); if (rc) return rc; }
 	CUDA_TRY(cudaEventRecord(W.e2, st));
 	rc = fetch_result(W, want, capacity, st, res); if (rc) return rc;
 	CUDA_TRY(cudaEventElapsedTime(&res->ms_front, W.e0, W.e1));
@@ -2014,6 +2157,7 @@ static int scan_stream_impl(const agb_desc &d, uint64_t n, const SliceSource &sr
 	CUDA_TRY(cudaEventRecord(W.e1, W.s_comp));
 	if (use_front) { rc = refine_launch(d, W, W.h2d_text, n, W.s_comp); if (rc) return rc; }
 	rc = records_launch(d, W, W.h2d_text, n, use_front, want, -1, W.h2d_rec, capacity, W.s_comp); if (rc) return rc;
+	if (want & AGB_WANT_ORDINALS) { rc = ordinals_launch(d, W, W.h2d_text, n, (want & AGB_WANT_RECORDS) ? W.h2d_rec : nullptr, capacity, W.s_comp); if (rc) return rc; }
 	CUDA_TRY(cudaEventRecord(W.e2, W.s_comp));
 	rc = fetch_result(W, want, capacity, W.s_comp, res); if (rc) return rc;
 	if (res->n_records) {

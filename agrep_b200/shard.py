@@ -52,9 +52,29 @@ def page_shards(total_bytes, world, page=4096):
     return [(r * per, per) for r in range(world)]
 
 
-def gather_records(recs, n_records, base, dist=None, group=None):
+def count_closes(text, delim=b"\n"):
+    """record closes of a text scanned on its own: delimiter ends at the virtual '\n', in the text and in the delimiter
+    appended at EOF -- what agb_result.n_closes reports (host restatement for the CPU tests)"""
+    L = len(delim)
+    ext = bytes(text) + bytes(delim)
+    n = sum(1 for q in range(len(ext)) if _delim_ends_at(ext, q, delim))
+    return n + (1 if (L == 1 and delim[0] == 0x0A) else 0)
+
+
+def ordinal_base(closes_before, rank, delim=b"\n"):
+    """what rank `rank` adds to its shard-local ordinals (the j that -n prints): the closes of the shards before it,
+    minus what those scans counted that the whole text does not have -- the delimiter appended at each shard's EOF
+    and, for the 1-byte '\n', this and every other later shard's virtual '\n' (it IS the '\n' that ended the
+    shard before)."""
+    virt = 1 if (len(delim) == 1 and delim[0] == 0x0A) else 0
+    return sum(closes_before) - rank * (1 + virt)
+
+
+def gather_records(recs, n_records, base, dist=None, group=None, closes=None, delim=b"\n"):
     """recs: int64 tensor [cap, 4] of (begin, end, ordinal, level) with shard-local offsets, n_records valid rows.
     Returns on every rank the concatenation over ranks, offsets made global (+ base) -- ordered because shards are.
+    closes: this shard's agb_result.n_closes; when given the ordinals are made global too (an exclusive
+    prefix sum over the ranks, riding on the same all_gather as the counts).
     Collectives: all_gather of the counts, all_gather of the lists padded to the longest (payload = 32 B/record)."""
     blk = recs[:n_records].clone()
     if n_records:
@@ -62,10 +82,14 @@ def gather_records(recs, n_records, base, dist=None, group=None):
     if dist is None or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return blk
     world = dist.get_world_size(group)
-    cnt = torch.tensor([n_records], dtype=torch.int64, device=recs.device)
-    allc = torch.zeros(world, dtype=torch.int64, device=recs.device)
+    rank = dist.get_rank(group)
+    cnt = torch.tensor([n_records, closes if closes is not None else 0], dtype=torch.int64, device=recs.device)
+    allc = torch.zeros(2 * world, dtype=torch.int64, device=recs.device)
     dist.all_gather_into_tensor(allc, cnt, group=group)
-    counts = [int(x) for x in allc.tolist()]
+    pairs = allc.view(world, 2).tolist()
+    counts = [int(x[0]) for x in pairs]
+    if closes is not None and n_records:
+        blk[:, 2] += ordinal_base([int(x[1]) for x in pairs[:rank]], rank, delim)
     m = max(counts)
     if m == 0:
         return blk

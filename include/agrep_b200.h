@@ -96,8 +96,9 @@ typedef struct agb_pattern agb_pattern;       /* opaque: agb_desc + bookkeeping 
  *   begin   = offset of lasti: first byte of the delimiter that closed the previous record; -1 for the
  *             virtual '\n' in front of the text (bitap.c:140), 0 when a user delimiter has not been seen yet
  *   end     = offset of print_end + 1 = first byte of the delimiter that closes this record
- *   ordinal = j at output() time; -n prints j-1 (agrep.c:3878); 0 from the scan calls, filled by
- *             agb_fill_ordinals() on the host copy of the text when -n is wanted
+ *   ordinal = j at output() time; -n prints j-1 (agrep.c:3878); filled on the device when the scan is asked for
+ *             AGB_WANT_ORDINALS (one more pass over the text that counts delimiters), else 0;
+ *             agb_fill_ordinals() computes the same on a host copy of the text
  *   level   = smallest matching error level in best-match scans, else k                                */
 typedef struct agb_record {
 	int64_t begin;
@@ -107,7 +108,7 @@ typedef struct agb_record {
 	int32_t pad;
 } agb_record;
 
-enum { AGB_WANT_COUNT = 0, AGB_WANT_RECORDS = 1, AGB_WANT_LEVELS = 4 };
+enum { AGB_WANT_COUNT = 0, AGB_WANT_RECORDS = 1, AGB_WANT_ORDINALS = 2, AGB_WANT_LEVELS = 4 };
 
 typedef struct agb_result {
 	uint64_t n_matched;       /* num_of_matched for this text                                 */
@@ -115,6 +116,8 @@ typedef struct agb_result {
 	uint64_t n_flagged;       /* 16-byte chunks the front-end passed to the record stage      */
 	uint64_t level_hist[AGB_MAXERR + 1];      /* AGB_WANT_LEVELS: records by smallest level   */
 	float    ms_front, ms_records;            /* device time of the two stages (CUDA events)  */
+	uint64_t n_closes;        /* AGB_WANT_ORDINALS: record closes in the whole text, the virtual '\n' included (j at EOF):
+	                             what a following shard adds to its ordinals      */
 } agb_result;
 
 /* ---- pattern front-end (host; mirrors checksg.c + preproce.c + maskgen.c) ---- */

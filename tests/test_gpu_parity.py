@@ -5,6 +5,7 @@ import json, os, random
 import pytest
 import _oracle, _corpus
 import agrep_b200 as ag
+from agrep_b200 import _lib
 from test_oracle_golden import G, CORPORA, text
 
 pytestmark = pytest.mark.gpu
@@ -115,6 +116,35 @@ def test_dense_forms_on_ragged_records():
     res, got = ag.Pattern("t[hx]ese", k=3, linenum=1).scan_host(data, levels=True)
     assert res.n_matched == cnt and list(res.level_hist)[:4] == hist[:4]
     assert [(b, e, l) for b, e, _, l in got] == [(b, e, l) for b, e, _, l in recs]
+
+
+@pytest.mark.parametrize("pattern,kw,corpus_kw", [
+    ("because each", dict(k=2, linenum=1), dict(nlines=2000, seed=31)),
+    ("the", dict(k=0, linenum=1, wordbound=1), dict(nlines=800, seed=32, trailing_newline=False)),
+    ("state", dict(k=1, linenum=1, delim="$$"), dict(nlines=1500, seed=33, paragraphs=True)),
+    ("world", dict(k=1, linenum=1, delim="the"), dict(nlines=600, seed=34)),
+    ("governmental", dict(k=5, linenum=1), dict(nlines=1500, seed=35)),
+    ("t[hx]e", dict(k=0, linenum=1), dict(nlines=3000, seed=36)),
+])
+def test_device_ordinals_reproduce_j(pattern, kw, corpus_kw):
+    """AGB_WANT_ORDINALS: the j that -n prints, counted on the device (k_delim_count + k_ordinals), against the
+    oracle's j (pinned to the reference's -n output) and against the host helper; Result.n_closes = j at EOF"""
+    data = _corpus.make_text(**corpus_kw)
+    a = _oracle.compile(pattern, **kw)
+    cnt, recs = _oracle.scan(a, data)
+    assert cnt > 0
+    p = ag.Pattern(pattern, **kw)
+    for d in (data, b"\n" + data, data + b"\n\n\n", (kw.get("delim", "") .replace("$$", "\n\n")).encode() + data):
+        cnt, recs = _oracle.scan(a, d)
+        res, got = p.scan_host(d, ordinals=True)
+        assert [(b, e, j) for b, e, j, _ in got] == [(b, e, j) for b, e, j in recs], (pattern, kw)
+        arr = (_lib.Record * max(cnt, 1))()
+        for i, (b, e, j) in enumerate(recs):
+            arr[i].begin, arr[i].end = b, e
+        _lib.lib().agb_fill_ordinals(p._h, d, len(d), arr, cnt)
+        assert [arr[i].ordinal for i in range(cnt)] == [j for _, _, j in recs]
+        # a second text appended behind this one continues the count: what a following shard adds (SURVEY 8e)
+        assert res.n_closes >= (recs[-1][2] if recs else 0)
 
 
 def test_wide_pattern_64bit_rows():

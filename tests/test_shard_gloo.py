@@ -25,10 +25,10 @@ def _worker(rank, world, port, text, pattern, kw, delim_bytes, q):
         t = torch.zeros((max(cnt, 1), 4), dtype=torch.int64)
         for i, (b, e, j) in enumerate(recs):
             t[i, 0], t[i, 1], t[i, 2] = b, e, j
-        allr = shard.gather_records(t, cnt, cuts[rank], dist)
+        allr = shard.gather_records(t, cnt, cuts[rank], dist, closes=shard.count_closes(part, delim_bytes), delim=delim_bytes)
         total = torch.tensor([cnt]); dist.all_reduce(total)
         if rank == 0:
-            q.put((int(total), [(int(x[0]), int(x[1])) for x in allr]))
+            q.put((int(total), [(int(x[0]), int(x[1]), int(x[2])) for x in allr]))
     finally:
         dist.destroy_process_group()
 
@@ -54,7 +54,9 @@ def test_newline_shards_gather_to_the_whole_answer(world):
     total, got = run_world(world, text, "because each", kw, b"\n")
     assert total == cnt
     # a shard's first record begins at its virtual '\n' (-1 + base) = the real '\n' before it in the whole text
-    assert got == [(b, e) for b, e, _ in recs]
+    assert [(b, e) for b, e, _ in got] == [(b, e) for b, e, _ in recs]
+    # -n ordinals: shard-local j + the closes of the shards before (an exclusive prefix sum over the ranks)
+    assert [j for _, _, j in got] == [j for _, _, j in recs]
 
 
 def test_paragraph_shards():
@@ -64,7 +66,8 @@ def test_paragraph_shards():
     cnt, recs = _oracle.scan(a, text)
     total, got = run_world(2, text, "state", kw, b"\n\n")
     assert total == cnt
-    assert [e for _, e in got] == [e for _, e, _ in recs]      # record ends are global; begins differ by the leading delimiter
+    assert [e for _, e, _ in got] == [e for _, e, _ in recs]   # record ends are global; begins differ by the leading delimiter
+    assert [j for _, _, j in got] == [j for _, _, j in recs]
 
 
 def test_cut_points_are_record_aligned():
