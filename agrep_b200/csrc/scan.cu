@@ -1492,35 +1492,41 @@ __device__ __forceinline__ uint32_t ord_count_seq(Reader &R, const OrdParams &P,
 __global__ void __launch_bounds__(ORD_THREADS) k_delim_count(const OrdParams P)
 {
 	__shared__ uint32_t s_warp[ORD_THREADS / 32];
-	const uint32_t tid = threadIdx.x, lane = tid & 31;
-	const int64_t n = (int64_t)P.n, limit = n + P.L;
-	const int64_t s0 = (int64_t)blockIdx.x * ORD_TILE + (int64_t)tid * ORD_PER, s1 = s0 + ORD_PER < limit ? s0 + ORD_PER : limit;
-	uint32_t cnt = 0;
-	if (s0 < limit) {
-		if (P.L == 1 && s0 + ORD_PER <= n) {
-			/* 16 bytes at a time: exact per-byte equality by SWAR (0x80 where the byte equals the delimiter) */
-			const uint32_t d4 = P.delim[0] * 0x01010101u;
+	const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const int64_t n = (int64_t)P.n, limit = n + P.L, tile0 = (int64_t)blockIdx.x * ORD_TILE;
+	uint32_t cnt = 0;                                           /* this thread's share of the tile */
+	if (P.L == 1 && tile0 + ORD_TILE <= n) {
+		/* a warp takes a 512-byte block per iteration, 16 bytes per lane (coalesced): exact per-byte equality by
+		 * SWAR (0x80 where the byte equals the delimiter), one warp reduction per block */
+		const uint32_t d4 = P.delim[0] * 0x01010101u;
 #pragma unroll
-			for (int v = 0; v < ORD_PER / 16; v++) {
-				const uint4 x = __ldg(reinterpret_cast<const uint4 *>(P.text + s0) + v);
-				const uint32_t xs[4] = { x.x, x.y, x.z, x.w };
+		for (int it = 0; it < ORD_TILE / ORD_BLOCK / (ORD_THREADS / 32); it++) {
+			const uint32_t blk = wid * (ORD_TILE / ORD_BLOCK / (ORD_THREADS / 32)) + it;
+			const uint4 x = __ldg(reinterpret_cast<const uint4 *>(P.text + tile0 + (int64_t)blk * ORD_BLOCK) + lane);
+			const uint32_t xs[4] = { x.x, x.y, x.z, x.w };
+			uint32_t c = 0;
 #pragma unroll
-				for (int w = 0; w < 4; w++) {
-					const uint32_t t = xs[w] ^ d4;
-					cnt += __popc(~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t | 0x7F7F7F7Fu));
-				}
+			for (int w = 0; w < 4; w++) {
+				const uint32_t t = xs[w] ^ d4;
+				c += __popc(~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t | 0x7F7F7F7Fu));
 			}
-		} else {
+			const uint32_t b = __reduce_add_sync(0xffffffffu, c);
+			if (lane == 0) P.blocks[(uint64_t)blockIdx.x * (ORD_TILE / ORD_BLOCK) + blk] = (uint16_t)b;
+			cnt += c;
+		}
+	} else {
+		/* other delimiters and the last tile: every thread walks its 128 bytes; 4 threads = one block */
+		const int64_t s0 = tile0 + (int64_t)tid * ORD_PER, s1 = s0 + ORD_PER < limit ? s0 + ORD_PER : limit;
+		if (s0 < limit) {
 			Reader R; R.init(P.text, P.n, P.delim, P.L);
 			cnt = ord_count_seq(R, P, s0, s1);
 		}
+		uint32_t b = cnt;
+		b += __shfl_xor_sync(0xffffffffu, b, 1); b += __shfl_xor_sync(0xffffffffu, b, 2);
+		if ((tid & 3) == 0) P.blocks[(uint64_t)blockIdx.x * (ORD_TILE / ORD_BLOCK) + (tid >> 2)] = (uint16_t)b;
 	}
-	/* 4 threads = one 512-byte block; 256 threads = the tile */
-	uint32_t b = cnt;
-	b += __shfl_xor_sync(0xffffffffu, b, 1); b += __shfl_xor_sync(0xffffffffu, b, 2);
-	if ((tid & 3) == 0) P.blocks[(uint64_t)blockIdx.x * (ORD_TILE / ORD_BLOCK) + (tid >> 2)] = (uint16_t)b;
-	uint32_t w = __reduce_add_sync(0xffffffffu, cnt);
-	if (lane == 0) s_warp[tid >> 5] = w;
+	const uint32_t w = __reduce_add_sync(0xffffffffu, cnt);
+	if (lane == 0) s_warp[wid] = w;
 	__syncthreads();
 	if (tid == 0) { uint32_t t = 0; for (int i = 0; i < ORD_THREADS / 32; i++) t += s_warp[i]; P.tiles[blockIdx.x] = t; }
 }
