@@ -1554,6 +1554,7 @@ struct Workspace {               /* grow-only device scratch, one per device */
 	uint64_t *cand = nullptr; uint32_t *cand_counts = nullptr; uint64_t *cand_offsets = nullptr; agb_record *cand_first = nullptr; size_t cand_cap = 0;
 	uint32_t *scan_sums = nullptr; uint64_t *scan_offs = nullptr; size_t scan_cap = 0;
 	uint16_t *ord_blocks = nullptr; size_t ord_blocks_cap = 0;     /* delimiter ends per 512-byte block (AGB_WANT_ORDINALS) */
+	int ord_virt = 0;                                              /* 1: the virtual '\n' closes a record of its own (1-byte '\n' delimiter) */
 	unsigned long long *totals = nullptr;          /* 16 counters */
 	unsigned long long *h_totals = nullptr;        /* pinned */
 	agb_desc *d_desc = nullptr; agb_desc h_desc_copy; bool desc_valid = false;
@@ -2012,6 +2013,7 @@ static int ordinals_launch(const agb_desc &d, Workspace &W, const void *d_text, 
 	P.records = d_records; P.totals = W.totals; P.capacity = capacity;
 	memcpy(P.delim, d.delim, AGB_MAXDELIM + 2 < sizeof d.delim ? AGB_MAXDELIM + 2 : sizeof d.delim);
 	P.L = d.L; P.kind = d.delim_kind;
+	W.ord_virt = (d.L == 1 && d.delim[0] == '\n') ? 1 : 0;
 	/* bitap.c:151-156: j starts at -1 when the text begins with the user's delimiter (asearch0() has no such correction) */
 	P.j0 = (d.user_delim && d.engine != AGB_ENGINE_ASEARCH0 && n >= (uint64_t)d.L && memcmp(h_head, d.delim, (size_t)d.L) == 0) ? -1 : 0;
 	k_delim_count<<<(unsigned)tiles, ORD_THREADS, 0, st>>>(P); g_launches++;
@@ -2035,7 +2037,7 @@ static int fetch_result(Workspace &W, int want, uint64_t capacity, cudaStream_t 
 	res->n_flagged = W.h_totals[1];
 	for (int i = 0; i <= AGB_MAXERR; i++) res->level_hist[i] = W.h_totals[2 + i];
 	res->n_records = (want & AGB_WANT_RECORDS) ? std::min<uint64_t>(res->n_matched, capacity) : 0;
-	res->n_closes = (want & AGB_WANT_ORDINALS) ? W.h_totals[13] : 0;
+	res->n_closes = (want & AGB_WANT_ORDINALS) ? W.h_totals[13] + (uint64_t)W.ord_virt : 0;
 	return AGB_OK;
 }
 

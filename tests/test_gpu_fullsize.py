@@ -97,3 +97,40 @@ def test_sampled_windows_equal_oracle(corpus):
             r, rr = scan(ag.Pattern(p, **{k: bool(v) if k != "k" else v for k, v in kw.items()}), t, pg * PAGE, win, 1 << 18)
             assert r.n_matched == cnt, (p, pg)
             assert [(int(b), int(e)) for b, e in rr.tolist()] == [(b, e) for b, e, _ in orecs], (p, pg)
+
+
+def test_every_byte_forms_and_ordinals_at_full_size(corpus):
+    """the record stage that walks every byte (slices form: classes, -v, 'the') and the ordinals pass, at full size:
+    count(whole) == sum of count(part) over page-aligned parts; record closes add up the same way (each part counts
+    its own virtual '\\n' and the delimiter appended at its EOF, shard.ordinal_base); ordinals are the line numbers of
+    the generator: a record's ordinal is 1 + (newlines at or before its closing newline)."""
+    import torch
+    from agrep_b200 import shard
+    t, n = corpus
+    parts = 4
+    per = n // (PAGE * parts) * PAGE
+    spans = [(i * per, per if i < parts - 1 else n - per * (parts - 1)) for i in range(parts)]
+    for p, kw in (("t[hx]e", dict(k=0, linenum=True)), ("because each", dict(k=2, inverse=True, linenum=True)), ("the", dict())):
+        pat = ag.Pattern(p, **kw)
+        whole, _ = scan(pat, t, 0, n)
+        assert whole.n_matched == sum(scan(pat, t, o, l)[0].n_matched for o, l in spans), p
+    pat = ag.Pattern(NEEDLE, k=2, linenum=True)
+    cap = 1 << 22
+    recs = torch.zeros((cap, 4), dtype=torch.int64, device="cuda")
+    whole = pat.scan_device(t.data_ptr(), n, d_records=recs.data_ptr(), capacity=cap, ordinals=True)
+    ords = recs[:whole.n_records, 2].clone()
+    ends = recs[:whole.n_records, 1].clone()
+    assert bool((ords[1:] > ords[:-1]).all())
+    closes, got = [], []
+    for r, (o, l) in enumerate(spans):
+        res = pat.scan_device(t.data_ptr() + o, l, d_records=recs.data_ptr(), capacity=cap, ordinals=True)
+        got.append(recs[:res.n_records, 2].clone() + shard.ordinal_base(closes, r))
+        closes.append(int(res.n_closes))
+    assert bool((torch.cat(got) == ords).all())
+    assert whole.n_closes == sum(closes) - 2 * (parts - 1)
+    # against a direct count on a sample: newlines in [0, end] + the virtual one
+    for i in random.Random(3).sample(range(int(whole.n_records)), 8):
+        e = int(ends[i])
+        if e > (1 << 31):
+            continue
+        assert int(ords[i]) == int((t[:e + 1] == 10).sum().item()) + 1
