@@ -1080,7 +1080,7 @@ k_records_slices(const RecParams P)
 			_Pragma("unroll") for (int r = 0; r < NR; r++) S[r] = RS[r]; \
 		} while (0)
 
-		if (easy && !P.levels && !writing && !C.and_mode) {
+		if (easy && !P.levels && !C.and_mode) {
 			/* Plain counting away from both ends of the text: every record counts (agrep.c:3811 only bites at the ends).
 			 * No branch on a close: one would be taken by one or two lanes in almost every other step of a warp (a line
 			 * ends every ~60 bytes) and the divergence costs far more than it skips (measured: 260 cycles per step and
@@ -1116,7 +1116,20 @@ k_records_slices(const RecParams P)
 						first_j = (int)jb + sft; first_found = ((fw >> (31 - sft)) & 1u) != 0;
 						hits &= ~(0x80000000u >> sft);
 					}
-					cnt += __popc(hits);
+					if (writing) {
+						/* the emit pass walks the closes of this word in order: every hit is a record [previous close, this close) */
+						int64_t bg = last_j >= 0 ? a + last_j + 1 - L : 0;       /* (the first close of the slice is never a hit here) */
+						for (uint32_t c = cw; c; ) {
+							const int sft = __clz(c); const uint32_t bit = 0x80000000u >> sft;
+							const int64_t en = a + (int64_t)jb + sft + 1 - L;
+							if (hits & bit) {
+								const uint64_t at = out_pos + cnt;
+								if (at < P.capacity) { agb_record rec; rec.begin = bg; rec.end = en; rec.ordinal = 0; rec.level = C.k; rec.pad = 0; P.records[at] = rec; }
+								cnt++;
+							}
+							bg = en; c &= ~bit;
+						}
+					} else cnt += __popc(hits);
 					last_j = (int)jb + 32 - __ffs(cw);
 				}
 			}
