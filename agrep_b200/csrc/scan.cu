@@ -939,6 +939,17 @@ k_records_dense(const RecParams P)
 	}
 }
 
+/* how dense are the flags?  popcount of every `stride`-th bitmap word (an estimate is all the host needs to pick the
+ * record stage's form before it spends time on stage 1.5) */
+__global__ void __launch_bounds__(256) k_bitmap_sample(const uint32_t *bitmap, uint64_t n_words, uint32_t stride, unsigned long long *out)
+{
+	unsigned long long c = 0;
+	for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * stride; i < n_words; i += (uint64_t)gridDim.x * blockDim.x * stride)
+		c += __popc(bitmap[i]);
+	c = __reduce_add_sync(0xffffffffu, (uint32_t)c);
+	if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
 /* slices form: the automaton over EVERYTHING in lockstep.  The dense tile form above gives every thread whole
  * records, so a warp waits for its longest lane (16 of 32 lanes busy on text lines).  Here every thread walks a
  * fixed slice of SL_PER bytes, whatever the records do:
@@ -2002,6 +2013,23 @@ static int records_launch(const agb_desc &d, Workspace &W, const void *d_text, u
 	return AGB_OK;
 }
 
+/* after stage 1: is the bitmap so full that thinning it (stage 1.5) and walking a candidate list cannot pay?  Then the
+ * record stage walks every byte anyway (slices / dense tile form) and stage 1.5 is skipped.  Estimated from every
+ * 61st bitmap word; same 5 % threshold as the list/dense switch in records_launch(). */
+static int front_is_dense(Workspace &W, uint64_t n, cudaStream_t st, bool *dense)
+{
+	const uint64_t n_chunks = (n + 15) / 16, n_words = (n_chunks + 31) / 32;
+	const uint32_t stride = n_words > (1u << 16) ? 61u : 1u;
+	CUDA_TRY(cudaMemsetAsync(W.totals + 14, 0, sizeof(unsigned long long), st));
+	const uint64_t samples = (n_words + stride - 1) / stride;
+	const unsigned grid = (unsigned)std::min<uint64_t>((samples + 255) / 256, (uint64_t)W.sm_count * 8);
+	k_bitmap_sample<<<grid ? grid : 1, 256, 0, st>>>(W.bitmap, n_words, stride, W.totals + 14); g_launches++;
+	CUDA_TRY(cudaMemcpyAsync(W.h_totals + 14, W.totals + 14, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	*dense = W.h_totals[14] * stride > n_chunks / 20 + 1024;
+	return AGB_OK;
+}
+
 /* AGB_WANT_ORDINALS: fill agb_record.ordinal of the list just written and leave the number of record closes of the
  * whole text (j after the last record, the basis of the next shard's ordinals) in totals[13].  Runs after the
  * record stage, whose tile scratch it reuses. */
@@ -2069,9 +2097,10 @@ static int scan_device_impl(const agb_desc &d, const void *d_text, uint64_t n, i
 	rc = ws_upload_desc(W, d, st); if (rc) return rc;
 	CUDA_TRY(cudaMemsetAsync(W.totals, 0, 16 * sizeof(unsigned long long), st));
 	CUDA_TRY(cudaEventRecord(W.e0, st));
-	const bool use_front = front_usable(d) && n > 0;
+	bool use_front = front_usable(d) && n > 0;
 	if (use_front) { rc = front_launch(d, W, d_text, n, 0, ~0ull, false, st); if (rc) return rc; }
 	CUDA_TRY(cudaEventRecord(W.e1, st));
+	if (use_front) { bool dense = false; rc = front_is_dense(W, n, st, &dense); if (rc) return rc; if (dense) use_front = false; }
 	if (use_front) { rc = refine_launch(d, W, d_text, n, st); if (rc) return rc; }
 	rc = records_launch(d, W, d_text, n, use_front, want, want_level, d_records, capacity, st); if (rc) return rc;
 	if (want & AGB_WANT_ORDINALS) { rc = ordinals_launch(d, W, d_text, n, (want & AGB_WANT_RECORDS) ? d_records : nullptr, capacity, st); if (rc) return rc; }
@@ -2176,8 +2205,10 @@ static int scan_stream_impl(const agb_desc &d, uint64_t n, const SliceSource &sr
 		if (use_front) { rc = front_launch(d, W, W.h2d_text, n, (n_slices - 1) * words_per_slice, ~0ull, true, W.s_comp); if (rc) return rc; }
 	}
 	CUDA_TRY(cudaEventRecord(W.e1, W.s_comp));
-	if (use_front) { rc = refine_launch(d, W, W.h2d_text, n, W.s_comp); if (rc) return rc; }
-	rc = records_launch(d, W, W.h2d_text, n, use_front, want, -1, W.h2d_rec, capacity, W.s_comp); if (rc) return rc;
+	bool use_bitmap = use_front;
+	if (use_bitmap) { bool dense = false; rc = front_is_dense(W, n, W.s_comp, &dense); if (rc) return rc; if (dense) use_bitmap = false; }
+	if (use_bitmap) { rc = refine_launch(d, W, W.h2d_text, n, W.s_comp); if (rc) return rc; }
+	rc = records_launch(d, W, W.h2d_text, n, use_bitmap, want, -1, W.h2d_rec, capacity, W.s_comp); if (rc) return rc;
 	if (want & AGB_WANT_ORDINALS) { rc = ordinals_launch(d, W, W.h2d_text, n, (want & AGB_WANT_RECORDS) ? W.h2d_rec : nullptr, capacity, W.s_comp); if (rc) return rc; }
 	CUDA_TRY(cudaEventRecord(W.e2, W.s_comp));
 	rc = fetch_result(W, want, capacity, W.s_comp, res); if (rc) return rc;
