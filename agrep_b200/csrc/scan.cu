@@ -184,6 +184,12 @@ static int records_launch(const agb_desc &d, Workspace &W, const void *d_text, u
 	return AGB_OK;
 }
 
+/* an exact pattern that is no longer than its anchor ('the'): every chunk stage 1 flags holds a real occurrence, so
+ * stage 1.5 has nothing to remove -- if such flags are dense (front_is_dense), the record stage walks every byte
+ * anyway and stages 1.5 and the compaction are skipped.  For every other pattern only stage 1.5 can tell (a k = 4
+ * pattern of common words flags 8 % of the chunks and keeps none), so the decision waits for the list length. */
+static bool refine_cannot_thin(const agb_desc &d) { return d.k == 0 && d.n_anchors == 1 && d.pat_len <= d.anchor_len; }
+
 static int fetch_result(Workspace &W, int want, uint64_t capacity, cudaStream_t st, agb_result *res)
 {
 	CUDA_TRY(cudaMemcpyAsync(W.h_totals, W.totals, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -214,7 +220,7 @@ static int scan_device_impl(const agb_desc &d, const void *d_text, uint64_t n, i
 	bool use_front = front_usable(d) && n > 0;
 	if (use_front) { rc = front_launch(d, W, d_text, n, 0, ~0ull, false, st); if (rc) return rc; }
 	CUDA_TRY(cudaEventRecord(W.e1, st));
-	if (use_front) { bool dense = false; rc = front_is_dense(W, n, st, &dense); if (rc) return rc; if (dense) use_front = false; }
+	if (use_front && refine_cannot_thin(d)) { bool dense = false; rc = front_is_dense(W, n, st, &dense); if (rc) return rc; if (dense) use_front = false; }
 	if (use_front) { rc = refine_launch(d, W, d_text, n, st); if (rc) return rc; }
 	rc = records_launch(d, W, d_text, n, use_front, want, want_level, d_records, capacity, st); if (rc) return rc;
 	if (want & AGB_WANT_ORDINALS) { rc = ordinals_launch(d, W, d_text, n, (want & AGB_WANT_RECORDS) ? d_records : nullptr, capacity, st); if (rc) return rc; }
@@ -320,7 +326,7 @@ static int scan_stream_impl(const agb_desc &d, uint64_t n, const SliceSource &sr
 	}
 	CUDA_TRY(cudaEventRecord(W.e1, W.s_comp));
 	bool use_bitmap = use_front;
-	if (use_bitmap) { bool dense = false; rc = front_is_dense(W, n, W.s_comp, &dense); if (rc) return rc; if (dense) use_bitmap = false; }
+	if (use_bitmap && refine_cannot_thin(d)) { bool dense = false; rc = front_is_dense(W, n, W.s_comp, &dense); if (rc) return rc; if (dense) use_bitmap = false; }
 	if (use_bitmap) { rc = refine_launch(d, W, W.h2d_text, n, W.s_comp); if (rc) return rc; }
 	rc = records_launch(d, W, W.h2d_text, n, use_bitmap, want, -1, W.h2d_rec, capacity, W.s_comp); if (rc) return rc;
 	if (want & AGB_WANT_ORDINALS) { rc = ordinals_launch(d, W, W.h2d_text, n, (want & AGB_WANT_RECORDS) ? W.h2d_rec : nullptr, capacity, W.s_comp); if (rc) return rc; }
