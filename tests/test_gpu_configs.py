@@ -48,3 +48,19 @@ def test_config3_bestmatch_sweep_case_insensitive():
                 break
         best, res = ag.bestmatch_device(P20, t.data_ptr(), n, nocase=1)
         assert (best, res.n_matched) == want, (maxedits, every, best, res.n_matched, want)
+
+
+def test_the_record_stage_gets_few_chunks_when_the_filters_can_thin():
+    """which form runs is a performance decision, not a parity one -- so it gets its own check: n_flagged is the number
+    of chunks handed to the record stage.  Patterns of common words flag several per cent of the chunks in stage 1;
+    stage 1.5 must still run and leave almost nothing (a shortcut that sent the k=4 case to the every-byte form cost
+    6x), while an exact short literal that is everywhere goes to the every-byte form directly."""
+    n = 16384 * PAGE                                  # 64 MiB
+    host = ag.corpus_host(n, needle="because each", needle_every=4096, needle_maxedits=3)
+    chunks = n // 16
+    for pat, kw in (("because each just those", dict(k=4, nocase=True, linenum=True)), ("because each", dict(k=2)),
+                    ("because each", dict(k=3)), ("government", dict())):
+        res, _ = ag.Pattern(pat, **kw).scan_host(host, want_records=False)
+        assert res.n_flagged < chunks // 20, (pat, kw, res.n_flagged, chunks)
+    res, _ = ag.Pattern("the").scan_host(host, want_records=False)
+    assert res.n_flagged == chunks
