@@ -19,6 +19,7 @@
  * Not for: patterns with '#' or -p (unbounded memory), run delimiters ($$: the pairing depends on the start of
  * the run): those keep the dense tile form. */
 
+#define SL_BATCH 8
 template <typename T, int NR, bool COSTS>
 __global__ void __launch_bounds__(SL_THREADS)
 k_records_slices(const RecParams P)
@@ -37,13 +38,21 @@ k_records_slices(const RecParams P)
 	const int L = C.L, warm = P.warm;
 	const int64_t limit = n + L;
 	/* ---- stage [tile0 - SL_APRON, tile_end): coalesced 16-byte loads, stored into the padded strips ---- */
-	for (uint32_t u = tid; u < (SL_APRON + SL_TILE) / 16; u += SL_THREADS) {
-		const int64_t g = tile0 - SL_APRON + (int64_t)u * 16;
-		if (g >= 0 && g < readable) {
-			const uint4 v = __ldg(reinterpret_cast<const uint4 *>(P.text + g));
-			const uint32_t x = (uint32_t)(g - tile0 + SL_PER);      /* byte number counted from the start of strip 0 */
+	/* (eight loads in flight per thread before the first store: the loop is latency-bound otherwise) */
+	for (uint32_t u0 = tid; u0 < (SL_APRON + SL_TILE) / 16; u0 += SL_BATCH * SL_THREADS) {
+		uint4 v[SL_BATCH]; bool ok[SL_BATCH];
+#pragma unroll
+		for (int b = 0; b < SL_BATCH; b++) {
+			const uint32_t u = u0 + b * SL_THREADS;
+			const int64_t g = tile0 - SL_APRON + (int64_t)u * 16;
+			ok[b] = u < (SL_APRON + SL_TILE) / 16 && g >= 0 && g < readable;
+			if (ok[b]) v[b] = __ldg(reinterpret_cast<const uint4 *>(P.text + g));
+		}
+#pragma unroll
+		for (int b = 0; b < SL_BATCH; b++) if (ok[b]) {
+			const uint32_t x = (u0 + b * SL_THREADS) * 16 + (SL_PER - SL_APRON);      /* byte number counted from the start of strip 0 */
 			uint32_t *dst = reinterpret_cast<uint32_t *>(s_text + (x >> 8) * SL_STRIDE + (x & (SL_PER - 1)));
-			dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+			dst[0] = v[b].x; dst[1] = v[b].y; dst[2] = v[b].z; dst[3] = v[b].w;
 		}
 	}
 	__syncthreads();
