@@ -280,6 +280,22 @@ __global__ void __launch_bounds__(ORD_THREADS) k_delim_count(const OrdParams P)
 	if (tid == 0) { uint32_t t = 0; for (int i = 0; i < ORD_THREADS / 32; i++) t += s_warp[i]; P.tiles[blockIdx.x] = t; }
 }
 
+/* the tile counts from block counts that stage 1 already took (front.cu, COUNT): 64 blocks per tile, plus the
+ * delimiter appended at EOF, which no block of the text has seen (position n; L = 1 on this path) */
+__global__ void __launch_bounds__(256) k_ord_tiles(const OrdParams P, uint64_t n_tiles)
+{
+	const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n_tiles) return;
+	const uint64_t b0 = t * (ORD_TILE / ORD_BLOCK), eof_blk = P.n / ORD_BLOCK;
+	uint32_t sum = 0;
+	for (uint32_t i = 0; i < ORD_TILE / ORD_BLOCK; i++) {
+		uint32_t v = P.blocks[b0 + i];
+		if (b0 + i == eof_blk) { v += 1; P.blocks[b0 + i] = (uint16_t)v; }
+		sum += v;
+	}
+	P.tiles[t] = sum;
+}
+
 __global__ void __launch_bounds__(256) k_ordinals(const OrdParams P)
 {
 	unsigned long long nrec = P.totals[0];
@@ -317,8 +333,21 @@ int front_is_dense(Workspace &W, uint64_t n, cudaStream_t st, bool *dense)
 /* AGB_WANT_ORDINALS: fill agb_record.ordinal of the list just written and leave the number of record closes of the
  * whole text (j after the last record, the basis of the next shard's ordinals) in totals[13].  Runs after the
  * record stage, whose tile scratch it reuses. */
+/* the block array of the ordinals pass: (n + L) / 512 entries, zeroed where stage 1 will not write */
+int ordinals_reserve(const agb_desc &d, Workspace &W, uint64_t n)
+{
+	const uint64_t limit = n + (uint64_t)d.L, tiles = (limit + ORD_TILE - 1) / ORD_TILE;
+	const size_t nb = (size_t)tiles * (ORD_TILE / ORD_BLOCK);
+	if (nb > W.ord_blocks_cap) {
+		if (W.ord_blocks) cudaFree(W.ord_blocks);
+		W.ord_blocks = nullptr; W.ord_blocks_cap = 0;
+		CUDA_TRY(cudaMalloc(&W.ord_blocks, nb * sizeof(uint16_t))); W.ord_blocks_cap = nb;
+	}
+	return AGB_OK;
+}
+
 int ordinals_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, agb_record *d_records,
-                           uint64_t capacity, cudaStream_t st)
+                           uint64_t capacity, cudaStream_t st, bool blocks_counted)
 {
 	uint8_t *h_head = reinterpret_cast<uint8_t *>(W.h_totals + 14);      /* pinned scratch: the first bytes of the text */
 	if (n >= (uint64_t)d.L && d.user_delim) {
@@ -327,12 +356,7 @@ int ordinals_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_
 	}
 	const uint64_t limit = n + (uint64_t)d.L, tiles = (limit + ORD_TILE - 1) / ORD_TILE;
 	if (tiles + 1 > W.tiles) return AGB_ERR_NOMEM;                       /* (ws_prepare sized them for n + one tile) */
-	const size_t nb = (size_t)tiles * (ORD_TILE / ORD_BLOCK);
-	if (nb > W.ord_blocks_cap) {
-		if (W.ord_blocks) cudaFree(W.ord_blocks);
-		W.ord_blocks = nullptr; W.ord_blocks_cap = 0;
-		CUDA_TRY(cudaMalloc(&W.ord_blocks, nb * sizeof(uint16_t))); W.ord_blocks_cap = nb;
-	}
+	{ int rc0 = ordinals_reserve(d, W, n); if (rc0) return rc0; }
 	OrdParams P; memset(&P, 0, sizeof P);
 	P.text = (const uint8_t *)d_text; P.n = n; P.blocks = W.ord_blocks; P.tiles = W.tile_counts; P.tile_off = W.tile_offsets;
 	P.records = d_records; P.totals = W.totals; P.capacity = capacity;
@@ -341,7 +365,8 @@ int ordinals_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_
 	W.ord_virt = (d.L == 1 && d.delim[0] == '\n') ? 1 : 0;
 	/* bitap.c:151-156: j starts at -1 when the text begins with the user's delimiter (asearch0() has no such correction) */
 	P.j0 = (d.user_delim && d.engine != AGB_ENGINE_ASEARCH0 && n >= (uint64_t)d.L && memcmp(h_head, d.delim, (size_t)d.L) == 0) ? -1 : 0;
-	k_delim_count<<<(unsigned)tiles, ORD_THREADS, 0, st>>>(P); g_launches++;
+	if (blocks_counted) { k_ord_tiles<<<(unsigned)((tiles + 255) / 256), 256, 0, st>>>(P, tiles); g_launches++; }     /* stage 1 counted the blocks */
+	else { k_delim_count<<<(unsigned)tiles, ORD_THREADS, 0, st>>>(P); g_launches++; }
 	k_scan_tiles<<<1, 1024, 0, st>>>(W.tile_counts, W.tile_offsets, tiles, W.totals + 13); g_launches++;
 	if (d_records && capacity) {
 		/* the list length is on the device (totals[0]); one thread per possible entry, bounded by the capacity */

@@ -47,8 +47,8 @@ __device__ __forceinline__ uint32_t windows_test(uint32_t lo, uint32_t hi, const
 }
 
 /* the FRONT_CH chunks a thread takes from one stage; FULL = no chunk of the stage is near the end of the text */
-template <int NA, bool MASKED, bool FOLD, bool POLY, bool FULL>
-__device__ __forceinline__ void front_chunks(const FrontParams &P, const uint8_t *st, uint32_t tid, uint32_t lane, uint32_t rem, uint32_t *bm)
+template <int NA, bool MASKED, bool FOLD, bool POLY, bool FULL, bool COUNT>
+__device__ __forceinline__ void front_chunks(const FrontParams &P, const uint8_t *st, uint32_t tid, uint32_t lane, uint32_t rem, uint32_t *bm, uint16_t *nlb)
 {
 #pragma unroll
 	for (int c = 0; c < FRONT_CH; c++) {
@@ -57,6 +57,25 @@ __device__ __forceinline__ void front_chunks(const FrontParams &P, const uint8_t
 		/* the first word of the next chunk (a 4-way bank conflict, measured cheaper than SHFL + a predicated LDS:
 		 * 4905 vs 4787 GB/s, profiles/round1_front_variants.md) */
 		uint32_t x4 = *reinterpret_cast<const uint32_t *>(st + idx * 16 + 16);
+		if (COUNT) {
+			/* -n: the delimiter bytes of this chunk (SWAR: 0x80 where a byte equals the delimiter), summed over the warp =
+			 * one 512-byte block of the ordinals pass (aux.cu), which then need not read the text again */
+			const uint32_t xs[4] = { v.x, v.y, v.z, v.w };
+			uint32_t cn = 0;
+#pragma unroll
+			for (int w = 0; w < 4; w++) {
+				const uint32_t t = xs[w] ^ P.delim4;
+				uint32_t z = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t | 0x7F7F7F7Fu);
+				if (!FULL) {                                     /* only bytes of the text */
+					/* rem chunks are left from the start of the stage, the last one padded: bytes of this word inside the text */
+					const int64_t valid = ((int64_t)rem - (int64_t)idx) * 16 - (int64_t)(P.n_chunks * 16 - P.n) - 4 * w;
+					if (valid <= 0) z = 0; else if (valid < 4) z &= (1u << (8 * (uint32_t)valid)) - 1u;
+				}
+				cn += __popc(z);
+			}
+			const uint32_t blk = __reduce_add_sync(0xffffffffu, cn);
+			if (lane == 0 && (FULL || idx < rem)) nlb[c * (FRONT_THREADS / 32)] = (uint16_t)blk;
+		}
 		if (FOLD) { v.x |= P.fold; v.y |= P.fold; v.z |= P.fold; v.w |= P.fold; x4 |= P.fold; }
 		uint32_t acc = 0xffffffffu;
 		acc = windows_test<NA, MASKED, POLY>(v.x, v.y, P, acc);
@@ -80,7 +99,7 @@ __device__ __forceinline__ void front_chunks(const FrontParams &P, const uint8_t
  * ring, each completing on its own mbarrier; all 256 threads take 4 chunks per stage from shared memory
  * (LDS.128, conflict-free: a warp reads 512 consecutive bytes), test the 16 windows of each chunk and ballot
  * the 32 verdicts of a warp into one bitmap word.  Every text byte crosses HBM->SM once. */
-template <int NA, bool MASKED, bool FOLD, bool POLY>
+template <int NA, bool MASKED, bool FOLD, bool POLY, bool COUNT>
 __global__ void __launch_bounds__(FRONT_THREADS, FRONT_CTAS_PER_SM)
 k_front(const FrontParams P)
 {
@@ -115,23 +134,30 @@ k_front(const FrontParams P)
 		uint32_t *bm = P.bitmap + sg * FRONT_WORDS_PER_STAGE + warp_in_cta;
 		/* full = every chunk of the stage exists and none is among the last two of the text: no per-chunk EOF logic */
 		const bool full = left >= FRONT_STAGE_CHUNKS + 2;
-		if (full) front_chunks<NA, MASKED, FOLD, POLY, true>(P, st, tid, lane, rem, bm);
-		else front_chunks<NA, MASKED, FOLD, POLY, false>(P, st, tid, lane, rem, bm);
+		uint16_t *nlb = COUNT ? P.nl_blocks + sg * FRONT_WORDS_PER_STAGE + warp_in_cta : nullptr;
+		if (full) front_chunks<NA, MASKED, FOLD, POLY, true, COUNT>(P, st, tid, lane, rem, bm, nlb);
+		else front_chunks<NA, MASKED, FOLD, POLY, false, COUNT>(P, st, tid, lane, rem, bm, nlb);
 		__syncthreads();                       /* everyone is done reading this slot */
 		if (tid == 0) issue((uint64_t)it + FRONT_NST);   /* refill it with the stage FRONT_NST iterations ahead */
 	}
 }
 
-template <int NA, bool MASKED, bool FOLD, bool POLY>
-static void launch_front_one(const FrontParams &P, unsigned grid, cudaStream_t st)
+template <int NA, bool MASKED, bool FOLD, bool POLY, bool COUNT>
+static void launch_front_cnt(const FrontParams &P, unsigned grid, cudaStream_t st)
 {
 	static bool configured[64] = {false};
 	int dev = 0; cudaGetDevice(&dev);
 	if (!configured[dev & 63]) {
-		cudaFuncSetAttribute(k_front<NA, MASKED, FOLD, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, FRONT_SMEM);
+		cudaFuncSetAttribute(k_front<NA, MASKED, FOLD, POLY, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FRONT_SMEM);
 		configured[dev & 63] = true;
 	}
-	k_front<NA, MASKED, FOLD, POLY><<<grid, FRONT_THREADS, FRONT_SMEM, st>>>(P);
+	k_front<NA, MASKED, FOLD, POLY, COUNT><<<grid, FRONT_THREADS, FRONT_SMEM, st>>>(P);
+}
+template <int NA, bool MASKED, bool FOLD, bool POLY>
+static void launch_front_one(const FrontParams &P, unsigned grid, cudaStream_t st)
+{
+	if (P.nl_blocks) launch_front_cnt<NA, MASKED, FOLD, POLY, true>(P, grid, st);
+	else launch_front_cnt<NA, MASKED, FOLD, POLY, false>(P, grid, st);
 }
 template <int NA, bool POLY>
 static void launch_front_na(const FrontParams &P, bool masked, bool fold, unsigned grid, cudaStream_t st)
@@ -163,7 +189,7 @@ bool front_usable(const agb_desc &d) { return d.plan == AGB_PLAN_ANCHORS && d.n_
 /* stage 1 over bitmap words [word_begin, word_end) of a text of n bytes; word_begin must be a multiple of 32
  * (a stage is 32 words).  slack16: 16 more bytes after the last chunk are readable (true for our own buffers). */
 int front_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n,
-                        uint64_t word_begin, uint64_t word_end, bool slack16, cudaStream_t st)
+                        uint64_t word_begin, uint64_t word_end, bool slack16, cudaStream_t st, bool count_delims)
 {
 	const uint64_t n_chunks = (n + 15) / 16, n_words = (n_chunks + 31) / 32;
 	if (word_end > n_words) word_end = n_words;
@@ -174,6 +200,7 @@ int front_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n
 	F.stage_begin = word_begin / FRONT_WORDS_PER_STAGE;
 	F.stage_end = (word_end + FRONT_WORDS_PER_STAGE - 1) / FRONT_WORDS_PER_STAGE;
 	F.fold = d.anchor_fold; F.amask = d.anchor_mask;
+	F.nl_blocks = count_delims ? W.ord_blocks : nullptr; F.delim4 = d.delim[0] * 0x01010101u;
 	const uint64_t stages = F.stage_end - F.stage_begin;
 	unsigned grid = (unsigned)std::min<uint64_t>(stages, (uint64_t)W.sm_count * FRONT_CTAS_PER_SM);
 	if (!grid) grid = 1;

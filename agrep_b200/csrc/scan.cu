@@ -202,6 +202,16 @@ static int fetch_result(Workspace &W, int want, uint64_t capacity, cudaStream_t 
 	return AGB_OK;
 }
 
+/* the block counters stage 1 fills when it counts delimiters: allocated, and zeroed behind the last bitmap word
+ * (the tile sums read whole tiles; the block of the delimiter appended at EOF may lie there) */
+static int ordinals_prepare_blocks(const agb_desc &d, Workspace &W, uint64_t n, cudaStream_t st)
+{
+	int rc = ordinals_reserve(d, W, n); if (rc) return rc;
+	const uint64_t n_words = ((n + 15) / 16 + 31) / 32;
+	if (W.ord_blocks_cap > n_words) CUDA_TRY(cudaMemsetAsync(W.ord_blocks + n_words, 0, (W.ord_blocks_cap - n_words) * sizeof(uint16_t), st));
+	return AGB_OK;
+}
+
 static int scan_device_impl(const agb_desc &d, const void *d_text, uint64_t n, int want, int want_level,
                             agb_record *d_records, uint64_t capacity, cudaStream_t st, agb_result *res)
 {
@@ -218,12 +228,15 @@ static int scan_device_impl(const agb_desc &d, const void *d_text, uint64_t n, i
 	CUDA_TRY(cudaMemsetAsync(W.totals, 0, 16 * sizeof(unsigned long long), st));
 	CUDA_TRY(cudaEventRecord(W.e0, st));
 	bool use_front = front_usable(d) && n > 0;
-	if (use_front) { rc = front_launch(d, W, d_text, n, 0, ~0ull, false, st); if (rc) return rc; }
+	/* -n with a 1-byte delimiter: stage 1 reads every byte anyway and counts the delimiters of each 512-byte block */
+	const bool count_in_front = use_front && (want & AGB_WANT_ORDINALS) && d.L == 1;
+	if (count_in_front) { rc = ordinals_prepare_blocks(d, W, n, st); if (rc) return rc; }
+	if (use_front) { rc = front_launch(d, W, d_text, n, 0, ~0ull, false, st, count_in_front); if (rc) return rc; }
 	CUDA_TRY(cudaEventRecord(W.e1, st));
 	if (use_front && refine_cannot_thin(d)) { bool dense = false; rc = front_is_dense(W, n, st, &dense); if (rc) return rc; if (dense) use_front = false; }
 	if (use_front) { rc = refine_launch(d, W, d_text, n, st); if (rc) return rc; }
 	rc = records_launch(d, W, d_text, n, use_front, want, want_level, d_records, capacity, st); if (rc) return rc;
-	if (want & AGB_WANT_ORDINALS) { rc = ordinals_launch(d, W, d_text, n, (want & AGB_WANT_RECORDS) ? d_records : nullptr, capacity, st); if (rc) return rc; }
+	if (want & AGB_WANT_ORDINALS) { rc = ordinals_launch(d, W, d_text, n, (want & AGB_WANT_RECORDS) ? d_records : nullptr, capacity, st, count_in_front); if (rc) return rc; }
 	CUDA_TRY(cudaEventRecord(W.e2, st));
 	rc = fetch_result(W, want, capacity, st, res); if (rc) return rc;
 	CUDA_TRY(cudaEventElapsedTime(&res->ms_front, W.e0, W.e1));
@@ -290,6 +303,8 @@ static int scan_stream_impl(const agb_desc &d, uint64_t n, const SliceSource &sr
 	const bool direct = src.mem && src.pinned;
 	if (!direct && n && !W.stage[0]) for (int i = 0; i < STAGE_BUFS; i++) CUDA_TRY(cudaMallocHost(&W.stage[i], H2D_SLICE));
 	const bool use_front = front_usable(d) && n > 0;
+	const bool count_in_front = use_front && (want & AGB_WANT_ORDINALS) && d.L == 1;
+	if (count_in_front) { rc = ordinals_prepare_blocks(d, W, n, W.s_comp); if (rc) return rc; }
 	const uint64_t words_per_slice = H2D_SLICE / 512, n_slices = (n + H2D_SLICE - 1) / H2D_SLICE;
 	CUDA_TRY(cudaMemsetAsync(W.totals, 0, 16 * sizeof(unsigned long long), W.s_comp));
 	CUDA_TRY(cudaEventRecord(W.e0, W.s_comp));
@@ -317,19 +332,19 @@ static int scan_stream_impl(const agb_desc &d, uint64_t n, const SliceSource &sr
 		/* stage 1 on the previous slice: its last chunk looks 4 bytes into this one, which is now on its way */
 		if (use_front) {
 			CUDA_TRY(cudaStreamWaitEvent(W.s_comp, W.ev_copy[sb], 0));
-			if (i > 0) { rc = front_launch(d, W, W.h2d_text, n, (i - 1) * words_per_slice, i * words_per_slice, true, W.s_comp); if (rc) return rc; }
+			if (i > 0) { rc = front_launch(d, W, W.h2d_text, n, (i - 1) * words_per_slice, i * words_per_slice, true, W.s_comp, count_in_front); if (rc) return rc; }
 		}
 	}
 	if (n_slices) {
 		CUDA_TRY(cudaStreamWaitEvent(W.s_comp, W.ev_copy[(n_slices - 1) % STAGE_BUFS], 0));
-		if (use_front) { rc = front_launch(d, W, W.h2d_text, n, (n_slices - 1) * words_per_slice, ~0ull, true, W.s_comp); if (rc) return rc; }
+		if (use_front) { rc = front_launch(d, W, W.h2d_text, n, (n_slices - 1) * words_per_slice, ~0ull, true, W.s_comp, count_in_front); if (rc) return rc; }
 	}
 	CUDA_TRY(cudaEventRecord(W.e1, W.s_comp));
 	bool use_bitmap = use_front;
 	if (use_bitmap && refine_cannot_thin(d)) { bool dense = false; rc = front_is_dense(W, n, W.s_comp, &dense); if (rc) return rc; if (dense) use_bitmap = false; }
 	if (use_bitmap) { rc = refine_launch(d, W, W.h2d_text, n, W.s_comp); if (rc) return rc; }
 	rc = records_launch(d, W, W.h2d_text, n, use_bitmap, want, -1, W.h2d_rec, capacity, W.s_comp); if (rc) return rc;
-	if (want & AGB_WANT_ORDINALS) { rc = ordinals_launch(d, W, W.h2d_text, n, (want & AGB_WANT_RECORDS) ? W.h2d_rec : nullptr, capacity, W.s_comp); if (rc) return rc; }
+	if (want & AGB_WANT_ORDINALS) { rc = ordinals_launch(d, W, W.h2d_text, n, (want & AGB_WANT_RECORDS) ? W.h2d_rec : nullptr, capacity, W.s_comp, count_in_front); if (rc) return rc; }
 	CUDA_TRY(cudaEventRecord(W.e2, W.s_comp));
 	rc = fetch_result(W, want, capacity, W.s_comp, res); if (rc) return rc;
 	if (res->n_records) {

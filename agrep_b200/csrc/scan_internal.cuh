@@ -47,6 +47,8 @@ struct FrontParams {
 	uint32_t     one, scale;     /* 1 (kept opaque so the first Horner step stays an IMAD) and 256^(4-anchor_len) */
 	uint32_t     anchor[AGB_MAXANCHOR];
 	uint32_t     coef[AGB_MAXANCHOR];   /* prod_i (x - anchor[i]) mod 2^32, low order first, leading 1 implied */
+	uint16_t    *nl_blocks;      /* COUNT: delimiter bytes per 512-byte block = per bitmap word (the ordinals' first pass, fused) */
+	uint32_t     delim4;         /* the 1-byte delimiter, four times */
 };
 #define FRONT_SMEM (FRONT_NST * FRONT_SLOT_BYTES)
 
@@ -138,7 +140,7 @@ struct Workspace {               /* grow-only device scratch, one per device */
 /* front.cu */
 bool front_usable(const agb_desc &d);
 bool poly_setup(const uint32_t *a, int na, int bits, uint32_t *coef);
-int  front_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, uint64_t word_begin, uint64_t word_end, bool slack16, cudaStream_t st);
+int  front_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, uint64_t word_begin, uint64_t word_end, bool slack16, cudaStream_t st, bool count_delims = false);
 /* refine.cu */
 int  refine_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, cudaStream_t st);
 /* records.cu, slices.cu: one launch of the given form (count pass or emit pass, RecParams.emit) */
@@ -154,5 +156,6 @@ __global__ void k_scan_tiles(const uint32_t *counts, uint64_t *offsets, uint64_t
 __global__ void k_scan_partial(const uint32_t *counts, uint64_t n, uint32_t *block_sums);
 __global__ void k_scan_apply(const uint32_t *counts, uint64_t n, const uint64_t *block_offsets, uint64_t *offsets);
 int  front_is_dense(Workspace &W, uint64_t n, cudaStream_t st, bool *dense);
-int  ordinals_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, agb_record *d_records, uint64_t capacity, cudaStream_t st);
+int  ordinals_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, agb_record *d_records, uint64_t capacity, cudaStream_t st, bool blocks_counted = false);
+int  ordinals_reserve(const agb_desc &d, Workspace &W, uint64_t n);
 #endif

@@ -244,7 +244,7 @@ def secondary_workloads(ag, torch, corpus, n_local, stream):
         t, r = bestn
         nr = int(r.n_records)
         ords = rec[:nr, 2]
-        out.append({"config": "the headline query with -n (AGB_WANT_RECORDS | AGB_WANT_ORDINALS): list + ordinals, one more pass that counts delimiters",
+        out.append({"config": "the headline query with -n (AGB_WANT_RECORDS | AGB_WANT_ORDINALS): list + ordinals (stage 1 also counts the delimiters of every 512-byte block)",
                     "pattern": PATTERN, "bytes": n_local, "ms": t, "gb_s": n_local / t / 1e6, "matched": int(r.n_matched),
                     "n_closes": int(r.n_closes), "ordinals_increasing": bool(nr < 2 or bool((ords[1:] > ords[:-1]).all().item()))})
         del rec
