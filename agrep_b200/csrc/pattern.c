@@ -123,7 +123,14 @@ static int add_pattern(build_t *b, const unsigned char *s, int n, const agb_opti
 {
 	int i, esc;
 	for (i = 0; i < n; i++) {
-		if (s[i] == '\\') i++;                                                 /* preproce.c:139-142 */
+		if (s[i] == '\\') {                                                    /* preproce.c:139-142 */
+			/* a lone backslash at the very end escapes whatever preprocess() appended behind the pattern (the string
+			 * terminator, or the '<' of the -w/-x wrapper, preproce.c:148-175): not restated, refused */
+			if (++i >= n) {
+				if (o->wordbound || o->wholeline) FAIL("the pattern ends in a lone backslash");
+				n--;                                                           /* it escapes the terminator: nothing (the reference's strlen() stops there) */
+			}
+		}
 		else if (s[i] == '|' || s[i] == '*')
 			FAIL("regular expressions (re()/re1(), agrep.c:468-1917) are outside the accelerated scan path");
 	}
@@ -153,22 +160,30 @@ static int add_pattern(build_t *b, const unsigned char *s, int n, const agb_opti
 			i++;
 			if (i < n && s[i] == '^') { compl_ = 1; i++; }
 			lo = -1;
-			for (; i < n; i++) {
-				int cc = map_sym(s, &i, n, 1, &esc);
-				if (!esc && cc == S_RRANGE) { closed = 1; break; }
-				if (!esc && cc == S_HYPHEN) {                                  /* class[k-1] = next symbol */
-					int hi;
-					i++;
-					if (i >= n) break;
-					hi = map_sym(s, &i, n, 1, &esc);
-					if (o->nocase && is_upper(hi)) hi += 32;
-					if (lo >= 0) cls_range(p, lo, hi);
-					continue;
+			{   /* maskgen.c:104-116 keeps the class as (low, high) pairs: a symbol opens the pair (c, c), "-x" replaces the high
+			     * end of the last pair -- so a descending range like z-a matches nothing, not even z */
+				int plo[2 * WIDTH], phi[2 * WIDTH], np = 0, q;
+				for (; i < n; i++) {
+					int cc = map_sym(s, &i, n, 1, &esc);
+					if (!esc && cc == S_RRANGE) { closed = 1; break; }
+					if (!esc && cc == S_HYPHEN) {                              /* class[k-1] = next symbol */
+						int hi;
+						i++;
+						if (i >= n) break;
+						hi = map_sym(s, &i, n, 1, &esc);
+						if (o->nocase && is_upper(hi)) hi += 32;
+						if (np > 0) phi[np - 1] = hi;
+						continue;
+					}
+					if (o->nocase && is_upper(cc)) cc += 32;                   /* Pattern[] is lower-cased as a whole */
+					if (np < 2 * WIDTH) { plo[np] = phi[np] = cc; np++; }
 				}
-				if (o->nocase && is_upper(cc)) cc += 32;                       /* Pattern[] is lower-cased as a whole */
-				lo = cc;
-				cls_range(p, cc, cc);
+				for (q = 0; q < np; q++) {
+					if (plo[q] == S_NOCARE) cls_range(p, S_NOCARE, S_NOCARE);   /* maskgen.c:242-246 looks at the low end first: '.' = any */
+					else if (plo[q] <= phi[q]) cls_range(p, plo[q], phi[q]);
+				}
 			}
+			(void)lo;
 			if (!closed) FAIL("unmatched '[', ']' (use \\[, \\] to search for [, ])");
 			if (compl_) { p->cls[0] = ~p->cls[0]; p->cls[1] = ~p->cls[1]; p->cls[2] = ~p->cls[2]; p->cls[3] = ~p->cls[3]; }
 			if (o->nocase) {                                                   /* maskgen.c:259-266: Mask[U] = Mask[u] */
@@ -282,6 +297,14 @@ int agbi_derive(agb_desc *d, char *err, size_t errlen)
 	if (L < 1 || L > AGB_MAXDELIM || d->M < L + 1 || d->M > WIDTH - 1) FAIL("bad descriptor (M=%d, L=%d)", d->M, L);
 	if (d->k < 0 || d->k > AGB_MAXERR) FAIL("bad descriptor (k=%d)", d->k);
 	if (!d->dendpos) FAIL("internal: delimiter end bit missing");
+	/* the device also recognises delimiters away from the automaton (record starts, ordinals), by their bytes: position p
+	 * of the delimiter must accept delim[p-1] and nothing else (-i with letters in the delimiter makes it accept both cases) */
+	for (p = 1; p <= L; p++) {
+		const uint64_t bit = 1ull << (d->M - p); int c;
+		for (c = 0; c < 256; c++)
+			if (((d->mask[c] & bit) != 0) != (c == d->delim[p - 1]))
+				FAIL("the delimiter matches more than its own bytes here (-i with letters in the delimiter): not supported by the device record search");
+	}
 	/* delimiter recognition away from the automaton (record-start search on the device) */
 	if (L == 1 || !has_border(d->delim, L)) d->delim_kind = 0;
 	else {
@@ -403,6 +426,10 @@ static int parse_delim(const agb_options *o, build_t *b, agb_desc *d, char *err,
 			p = new_pos(b);
 			if (c == '\n' || b->no_error) p->prot = 1;
 			cls_set(p, c);
+			/* -i lower-cases the WHOLE internal pattern, the delimiter included, and copies every lower-case mask to its
+			 * upper-case byte (maskgen.c:52-58, 259-266): 'x' and 'X' both end a record then.  Stated here as it is;
+			 * agbi_derive() refuses it, because the device finds delimiters by their bytes. */
+			if (o->nocase && is_alpha(c)) { cls_set(p, c | 32); cls_set(p, (c | 32) - 32); }
 			d->delim[d->L++] = (unsigned char)c;
 		}
 		b->no_error = 0; b->even--;                    /* the closing '>' */

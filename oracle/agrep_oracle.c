@@ -95,7 +95,8 @@ static int preprocess(const unsigned char *pat, const orc_opts *o, const char *d
 	old_d[L] = 0;
 	for (i = d_end; i < m; i++) {               /* preproce.c:238-332 */
 		switch (temp[i]) {
-		case '\\': i++; out[j++] = temp[i]; break;
+		case '\\': i++; if (temp[i] == 0) { i = m; break; }   /* a lone backslash at the end escapes the terminator: maskgen's strlen() stops there */
+			out[j++] = temp[i]; break;
 		case '#': out[j++] = WILDCD; break;
 		case '(': out[j++] = LPARENT; break;
 		case ')': out[j++] = RPARENT; break;

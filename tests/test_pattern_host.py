@@ -145,3 +145,54 @@ def test_fill_ordinals_reproduces_j(pattern, kw, corpus_kw):
         arr[i].begin, arr[i].end = b, e
     _lib.lib().agb_fill_ordinals(p._h, data, len(data), arr, cnt)
     assert [arr[i].ordinal for i in range(cnt)] == [j for _, _, j in recs]
+
+
+def test_random_patterns_product_front_end_equals_oracle_front_end():
+    """differential fuzz of two independent restatements of checksg + preprocess + maskgen: the product's host front-end
+    (agrep_b200/csrc/pattern.c) and the oracle's (oracle/agrep_oracle.c, pinned to the reference's dumps): same
+    accept/reject decision, same automaton words, same masks, for random patterns over letters and metacharacters."""
+    import random
+    rnd = random.Random(2026)
+    atoms = list("abcdeXYZ 09") + [".", "#", "[a-c]", "[^xy]", "<ab>", "\\.", "\\[", ",", ";", "^", "$", "[x\\-z]", "(", ")", "-", "~", "{", "]",
+                                   "[z-a]", "[#-e]", "\\", "<", ">", "\xe9", "\xc9"]     # (no bare "[": "[-" and "-]" are undefined behaviour in maskgen.c:106-109)
+    checked = rejected = 0
+    for _ in range(600):
+        pat = "".join(rnd.choice(atoms) for _ in range(rnd.randint(1, 12)))
+        kw = dict(k=rnd.choice([0, 0, 1, 2, 3, 5]), linenum=1)
+        if rnd.random() < 0.3: kw["nocase"] = 1
+        if rnd.random() < 0.2: kw["wordbound"] = 1
+        if rnd.random() < 0.1: kw["wholeline"] = 1
+        if rnd.random() < 0.15: kw["delim"] = rnd.choice(["$$", "ab", "\\.", "X"])
+        if rnd.random() < 0.1: kw["ins_free"] = 1
+        # a lone backslash at the very end escapes what preprocess() appended: the terminator (ignored by both, like the
+        # reference) or the '<' of the -w/-x wrapper (the oracle follows the reference's quirk, the product refuses)
+        stripped = pat.replace("\\\\", "")
+        if stripped.endswith("\\") and (kw.get("wordbound") or kw.get("wholeline")):
+            with pytest.raises(ag.AgrepError):
+                ag.Pattern(pat, **kw)
+            rejected += 1
+            continue
+        try:
+            a = _oracle.compile(pat, **kw)
+        except _oracle.OracleError:
+            with pytest.raises(ag.AgrepError):
+                ag.Pattern(pat, **kw)
+            rejected += 1
+            continue
+        if kw.get("nocase") and any(ch.isalpha() for ch in kw.get("delim", "")):
+            # the reference folds the delimiter too (-i -d X splits at 'x' and 'X', maskgen.c:52-58, 259-266): the
+            # oracle follows it, the product refuses the combination (DESIGN.md 2)
+            assert a.mask[ord("x")] == a.mask[ord("X")] or "X" not in kw["delim"]
+            with pytest.raises(ag.AgrepError, match="delimiter matches more than its own bytes"):
+                ag.Pattern(pat, **kw)
+            rejected += 1
+            continue
+        D = ag.Pattern(pat, **kw).desc
+        assert (D.M, D.L, D.k, D.and_mode, D.engine) == (a.M, a.L, a.k, a.and_mode, a.engine), (pat, kw)
+        for f in ("init0", "init1", "noerr", "endpos", "dendpos", "dmask", "wildmask"):
+            assert getattr(D, f) == getattr(a, f), (pat, kw, f)
+        lut = LUT if (a.engine == 0 and kw.get("nocase")) else list(range(256))     # bitap.c:171: the exact engine folds through LUT[]
+        assert [D.mask[c] for c in range(256)] == [a.mask[lut[c]] for c in range(256)], (pat, kw)
+        assert bytes(D.delim[:D.L]) == bytes(a.dpat[:a.L])
+        checked += 1
+    assert checked > 150 and rejected > 20, (checked, rejected)
