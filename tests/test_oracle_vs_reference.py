@@ -123,3 +123,61 @@ def test_pattern_too_long_matches_reference_limit():
         _oracle.compile("a" * 30, width=32, k=1, linenum=1)
     _oracle.compile("a" * 29, width=32, k=1, linenum=1)
     _oracle.compile("a" * 40, width=64, k=1, linenum=1)
+
+
+def test_random_metachar_differential(ref_agrep):
+    """random patterns with classes, '.', '#', <>, ',' and ';', anchors, under -i/-w/-v/-p/-S2 and user delimiters, on a
+    text shorter than one 48 KiB block (no block artefacts): ordinals of the matching lines (newline records), counts
+    (user delimiters: their records are not one per output line).  Cases the reference refuses are skipped."""
+    if not ref_agrep:
+        pytest.skip("reference binary not built")
+    base = _corpus.make_text(400, seed=5)
+    words = [w for w in base.decode().split() if w.isalpha()]
+    rnd = random.Random(31)
+
+    def rand_pattern():
+        w = (rnd.choice(words) + " " + rnd.choice(words))[:rnd.randint(3, 14)]
+        out = []
+        for ch in w:
+            r = rnd.random()
+            out.append("." if r < 0.08 else "[" + ch + "x]" if r < 0.12 else "[^q]" if r < 0.15 else "#" if r < 0.17
+                       else ch.upper() if r < 0.19 else ch)
+        p = "".join(out)
+        r = rnd.random()
+        return ("<" + p[:2] + ">" + p[2:] if r < 0.08 else p + "," + rnd.choice(words) if r < 0.14
+                else p + ";" + rnd.choice(words) if r < 0.20 else "^" + p if r < 0.24 else p + "$" if r < 0.28 else p)
+    compared = 0
+    for _ in range(160):
+        data = ("\n".join(base.decode().split("\n")[:rnd.randint(200, 390)]) + rnd.choice(["\n", "", "\n\n"])).encode()
+        pat = rand_pattern()
+        k = rnd.choice([0, 0, 1, 2, 3, 4, 6])
+        kw, args = dict(k=k, linenum=1), (["-%d" % k] if k else [])
+        for p_, key, flag in ((0.25, "nocase", "-i"), (0.15, "wordbound", "-w"), (0.1, "inverse", "-v"), (0.05, "ins_free", "-p")):
+            if rnd.random() < p_:
+                kw[key] = 1; args.append(flag)
+        if rnd.random() < 0.15:
+            kw["delim"] = rnd.choice(["$$", "e "]); args += ["-d", kw["delim"]]
+        if k and rnd.random() < 0.06:
+            kw["cost_s"] = 2; args.append("-S2")
+        try:
+            a = _oracle.compile(pat, width=32, **kw)
+        except _oracle.OracleError:
+            continue
+        cnt, recs = _oracle.scan(a, data)
+        if "delim" in kw:
+            out = run_ref(ref_agrep, ["-c", "-n"] + args + [pat], data).strip()
+            if out.isdigit():
+                assert int(out) == cnt, (pat, args)
+                compared += 1
+            continue
+        with tempfile.NamedTemporaryFile(suffix=".txt", delete=False) as f:
+            f.write(data)
+        try:
+            p = subprocess.run([ref_agrep, "-V0", "-n"] + args + [pat, f.name], capture_output=True, timeout=120)
+        finally:
+            os.unlink(f.name)
+        if p.returncode == 255 or p.stderr.strip():
+            continue
+        assert [r[2] - 1 for r in recs] == [int(m.group(1)) for m in re.finditer(rb"^(\d+): ", p.stdout, re.M)], (pat, args)
+        compared += 1
+    assert compared > 100
