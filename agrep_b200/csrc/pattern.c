@@ -299,6 +299,10 @@ int agbi_derive(agb_desc *d, char *err, size_t errlen)
 	if (!d->dendpos) FAIL("internal: delimiter end bit missing");
 	/* the device also recognises delimiters away from the automaton (record starts, ordinals), by their bytes: position p
 	 * of the delimiter must accept delim[p-1] and nothing else (-i with letters in the delimiter makes it accept both cases) */
+	/* -p (Init1 all ones, bitap.c:123) makes every position sticky, the delimiter's too: with a delimiter of two or more
+	 * bytes "a ... b" then closes a record like "ab" does.  One byte is fine (its only position is D_endpos itself). */
+	if (d->init1 == ~0ull && L > 1)
+		FAIL("-p with a delimiter of more than one byte is not supported (insertions inside the delimiter would be free too)");
 	for (p = 1; p <= L; p++) {
 		const uint64_t bit = 1ull << (d->M - p); int c;
 		for (c = 0; c < 256; c++)

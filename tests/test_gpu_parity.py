@@ -148,6 +148,52 @@ def test_device_ordinals_reproduce_j(pattern, kw, corpus_kw):
         assert res.n_closes == shard.count_closes(d, kw.get("delim", "\n").replace("$$", "\n\n").encode())
 
 
+def test_random_metachar_differential():
+    """random patterns with classes, '.', '#', <>, ',' and ';', anchors, under -i/-w/-v/-p/-x/-S2 and user delimiters:
+    the list with ordinals and the count-only call against the oracle (tools/gpu_fuzz.py is the longer version)."""
+    base = _corpus.make_text(3000, seed=5)
+    words = [w for w in base.decode().split() if w.isalpha()]
+    rnd = random.Random(404)
+
+    def rand_pattern():
+        w = (rnd.choice(words) + " " + rnd.choice(words))[:rnd.randint(3, 20)]
+        out = []
+        for ch in w:
+            r = rnd.random()
+            out.append("." if r < 0.08 else "[" + ch + "x]" if r < 0.12 else "[^q]" if r < 0.15 else "#" if r < 0.17
+                       else ch.upper() if r < 0.19 else ch)
+        p = "".join(out)
+        r = rnd.random()
+        return ("<" + p[:2] + ">" + p[2:] if r < 0.08 else p + "," + rnd.choice(words) if r < 0.14
+                else p + ";" + rnd.choice(words) if r < 0.20 else "^" + p if r < 0.24 else p + "$" if r < 0.28 else p)
+    done = 0
+    for _ in range(220):
+        data = ("\n".join(base.decode().split("\n")[:rnd.randint(1000, 2900)]) + rnd.choice(["\n", "", "\n\n"])).encode()
+        pat = rand_pattern()
+        kw = dict(k=rnd.choice([0, 0, 1, 2, 3, 4, 6, 8]))
+        if rnd.random() < 0.8: kw["linenum"] = 1
+        for p_, key in ((0.25, "nocase"), (0.15, "wordbound"), (0.1, "inverse"), (0.05, "ins_free"), (0.04, "wholeline")):
+            if rnd.random() < p_: kw[key] = 1
+        if rnd.random() < 0.15: kw["delim"] = rnd.choice(["$$", "e ", "ab", "\\."])
+        if kw["k"] and rnd.random() < 0.06: kw["cost_s"] = 2
+        try:
+            a = _oracle.compile(pat, **kw)
+        except _oracle.OracleError:
+            continue
+        try:
+            p = ag.Pattern(pat, **api_kw(kw))
+        except ag.AgrepError as e:
+            assert "delimiter" in str(e), (pat, kw, e)          # the two documented refusals (DESIGN.md 2)
+            continue
+        cnt, recs = _oracle.scan(a, data)
+        res, got = p.scan_host(data, ordinals=True)
+        keep = (lambda t: t[:3]) if a.engine != 4 else (lambda t: t[:2])      # sgrep/bm has no j
+        assert res.n_matched == cnt and [keep(t) for t in got] == [keep(t) for t in recs], (pat, kw)
+        assert p.scan_host(data, want_records=False)[0].n_matched == cnt, (pat, kw)
+        done += 1
+    assert done > 120
+
+
 def test_wide_pattern_64bit_rows():
     pat = "people how too little state good very make"      # 42 chars -> M = 44
     data = TEXT + b"xx people how too little state good very make yy\nxx people hxw too litle state good very make\n"
