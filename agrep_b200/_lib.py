@@ -42,7 +42,7 @@ class Record(C.Structure):
 class Result(C.Structure):
     _fields_ = [("n_matched", C.c_uint64), ("n_records", C.c_uint64), ("n_flagged", C.c_uint64),
                 ("level_hist", C.c_uint64 * (AGB_MAXERR + 1)), ("ms_front", C.c_float), ("ms_records", C.c_float),
-                ("n_closes", C.c_uint64)]
+                ("n_closes", C.c_uint64), ("truncated", C.c_uint32), ("pad", C.c_uint32)]
 
 
 class CorpusSpec(C.Structure):

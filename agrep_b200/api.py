@@ -57,12 +57,15 @@ class Pattern:
         ordinals: also fill Record.ordinal (the j that -n prints) and Result.n_closes on the device."""
         n = len(data)
         want = (WANT_RECORDS if want_records else WANT_COUNT) | (WANT_LEVELS if levels else 0) | (WANT_ORDINALS if ordinals else 0)
-        cap = (capacity if capacity is not None else n // 2 + 16) if want_records else 0
-        recs = (Record * cap)() if cap else None
-        res = Result()
+        cap = (capacity if capacity is not None else n // 64 + 4096) if want_records else 0
         buf = (C.c_char * n).from_buffer_copy(data) if n else None
-        rc = _lib.lib().agb_scan_host(self._h, buf, n, want, recs, cap, C.byref(res))
-        return self._finish(rc, res, recs, want)
+        while True:
+            recs = (Record * cap)() if cap else None
+            res = Result()
+            rc = _lib.lib().agb_scan_host(self._h, buf, n, want, recs, cap, C.byref(res))
+            if rc != 0 or not res.truncated or capacity is not None:
+                return self._finish(rc, res, recs, want)
+            cap = res.n_matched          # the list did not fit (Result.truncated): once more with exactly n_matched entries
 
     def scan_device(self, dev_ptr, n, stream=0, d_records=0, capacity=0, levels=False, ordinals=False):
         """dev_ptr: device address of n bytes (16-byte aligned, e.g. torch tensor .data_ptr())."""

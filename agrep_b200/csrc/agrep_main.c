@@ -74,10 +74,16 @@ static int scan_files(const agb_pattern *p, char **files, int nfiles, int counti
 		agb_result res; agb_record *recs = NULL; int before = num_of_matched, rc;
 		const int count_only = counting || COUNT || SILENT || FILENAMEONLY;
 		if (!hb) continue;
-		cap = count_only ? 0 : n / 2 + 16;
-		if (cap) recs = (agb_record *)malloc(cap * sizeof *recs);
-		rc = agb_scan_host(p, hb + 1, n, count_only ? AGB_WANT_COUNT : (AGB_WANT_RECORDS | AGB_WANT_ORDINALS)   /* output() needs j even without -n (agrep.c:3815) */, recs, cap, &res);
-		if (rc) { fprintf(stderr, "%s: scan failed: %s\n", prog, agb_last_error()); exit(255); }   /* no CPU fallback */
+		/* the list is sized from a guess; a scan that reports more matching records than fit (an empty record is a record:
+		 * -v on blank lines) is run again with exactly n_matched entries */
+		cap = count_only ? 0 : n / 64 + 65536;
+		for (;;) {
+			if (cap) { recs = (agb_record *)realloc(recs, cap * sizeof *recs); if (!recs) { fprintf(stderr, "%s: out of memory\n", prog); exit(255); } }
+			rc = agb_scan_host(p, hb + 1, n, count_only ? AGB_WANT_COUNT : (AGB_WANT_RECORDS | AGB_WANT_ORDINALS)   /* output() needs j even without -n (agrep.c:3815) */, recs, cap, &res);
+			if (rc) { fprintf(stderr, "%s: scan failed: %s\n", prog, agb_last_error()); exit(255); }   /* no CPU fallback */
+			if (!res.truncated) break;
+			cap = (size_t)res.n_matched;
+		}
 		if (FILENAMEONLY && !counting) num_of_matched += res.n_matched ? 1 : 0;   /* the scan stops at the first hit (bitap.c:184-210, sgrep.c:813-814) */
 		else if (count_only) num_of_matched += (int)res.n_matched;
 		else {

@@ -67,10 +67,24 @@ struct Reader {
 	}
 };
 
+/* the same reader in front of a stretch of the text that the thread has staged in shared memory: [lo, lo + len) comes
+ * from there (one LDS), everything else from the slow path above */
+struct WindowReader {
+	Reader R; const uint8_t *sm; int64_t lo; uint32_t len;
+	__device__ __forceinline__ void init(const uint8_t *t, uint64_t n_, const uint8_t *d, int L_) { R.init(t, n_, d, L_); sm = nullptr; lo = 0; len = 0; }
+	__device__ __forceinline__ int get(int64_t p)
+	{
+		const uint64_t o = (uint64_t)(p - lo);
+		if (o < (uint64_t)len) return sm[o];
+		return R.get(p);
+	}
+};
+
 /* is q (file offset, < n) the last byte of a delimiter that closes a record?  kind 0: every occurrence
  * does (no self overlap); kind 1 (c^L, e.g. $$): greedy, non-overlapping from the start of the run of c,
  * the virtual '\n' counting as part of the run (asearch.c:55-57 D_Mask + the reset at :181). */
-__device__ __forceinline__ bool delim_ends_at(Reader &R, int64_t q, const uint8_t *delim, int L, int kind)
+template <typename RD>
+__device__ __forceinline__ bool delim_ends_at(RD &R, int64_t q, const uint8_t *delim, int L, int kind)
 {
 	if (L == 1) return R.get(q) == delim[0];
 	if (kind == 0) {

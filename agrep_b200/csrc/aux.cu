@@ -92,8 +92,9 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *counts, uin
 
 /* two-level exclusive scan for long count arrays (the per-candidate counts of the list form):
  * k_scan_partial sums blocks of 16384 counts, k_scan_tiles scans those sums, k_scan_apply finishes each block */
-__global__ void __launch_bounds__(1024) k_scan_partial(const uint32_t *counts, uint64_t n, uint32_t *block_sums)
+__global__ void __launch_bounds__(1024) k_scan_partial(const uint32_t *counts, uint64_t n, uint32_t *block_sums, const unsigned long long *n_dev)
 {
+	if (n_dev && *n_dev < n) n = *n_dev;                    /* the length lives on the device; the grid covers the capacity */
 	__shared__ uint32_t s_w[32];
 	const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK;
 	uint32_t sum = 0;
@@ -105,8 +106,9 @@ __global__ void __launch_bounds__(1024) k_scan_partial(const uint32_t *counts, u
 	if (threadIdx.x < 32) { uint32_t v = __reduce_add_sync(0xffffffffu, s_w[threadIdx.x]); if (threadIdx.x == 0) block_sums[blockIdx.x] = v; }
 }
 
-__global__ void __launch_bounds__(1024) k_scan_apply(const uint32_t *counts, uint64_t n, const uint64_t *block_offsets, uint64_t *offsets)
+__global__ void __launch_bounds__(1024) k_scan_apply(const uint32_t *counts, uint64_t n, const uint64_t *block_offsets, uint64_t *offsets, const unsigned long long *n_dev)
 {
+	if (n_dev && *n_dev < n) n = *n_dev;
 	__shared__ unsigned long long s_warp[32];
 	__shared__ unsigned long long s_carry;
 	const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;

@@ -85,6 +85,22 @@ static unsigned char *slurp(int fd, const unsigned char *dpat, int L, size_t *n_
 	return hb;
 }
 
+/* a scan that wants the record list: the list is sized from a guess and, when the scan reports more matching records
+ * than fit (agb_result.truncated), once more with exactly n_matched entries -- an empty record is a record too, so no
+ * bound short of one entry per text byte is safe up front (the reference prints blank lines under -v) */
+static int scan_records(const agb_pattern *p, const unsigned char *text, size_t n, int want, agb_record **recs, agb_result *res)
+{
+	size_t cap = n / 64 + 65536; int rc;
+	for (;;) {
+		agb_record *r = (agb_record *)realloc(*recs, cap * sizeof **recs);
+		if (!r) return AGB_ERR_NOMEM;
+		*recs = r;
+		rc = agb_scan_host(p, text, n, want | AGB_WANT_RECORDS, r, cap, res);
+		if (rc || !res->truncated) return rc;
+		cap = (size_t)res->n_matched;
+	}
+}
+
 static int fail(const char *what)
 {
 	fprintf(stderr, "%s: %s: %s\n", Progname, what, agb_last_error());
@@ -140,7 +156,7 @@ static void plan_from_internal(const unsigned char *P, int L, int D, agb_desc *d
 static int scan_and_replay(char old_D_pat[], const unsigned char *Pattern, int fd, int M, int D, int engine)
 {
 	agb_desc d; agb_pattern *p = NULL; agb_result res; agb_record *recs = NULL;
-	unsigned char dpat[2 * AGB_MAXDELIM + 2], *hb; size_t n = 0, cap, i; int L, c, rc, ret = 0;
+	unsigned char dpat[2 * AGB_MAXDELIM + 2], *hb; size_t n = 0, i; int L, c, rc, ret = 0;
 	char err[256];
 	const uint64_t HI = 0xFFFFFFFF00000000ull;
 
@@ -171,19 +187,17 @@ static int scan_and_replay(char old_D_pat[], const unsigned char *Pattern, int f
 	hb = slurp(fd, dpat, L, &n);
 	if (!hb) { agb_pattern_free(p); fprintf(stderr, "%s: out of memory\n", Progname); errno = AGREP_ERROR; return -1; }
 
-	if (COUNT && !FILENAMEONLY) {                           /* output() would only count (agrep.c:3812-3813) */
+	if (COUNT && !FILENAMEONLY && fd != -1) {               /* output() would only count (agrep.c:3812-3813) */
 		rc = agb_scan_host(p, hb + 1, n, AGB_WANT_COUNT, NULL, 0, &res);
 		if (rc) ret = fail("scan");
 		else num_of_matched += (int)res.n_matched;
 		goto done;
 	}
-	cap = n / 2 + 16;                                       /* a record is at least one byte + delimiter */
-	recs = (agb_record *)malloc(cap * sizeof *recs);
-	if (!recs) { ret = -1; errno = AGREP_ERROR; goto done; }
-	rc = agb_scan_host(p, hb + 1, n, AGB_WANT_RECORDS | (LINENUM ? AGB_WANT_ORDINALS : 0), recs, cap, &res);   /* j for output() (-n) on the device */
+	rc = scan_records(p, hb + 1, n, LINENUM ? AGB_WANT_ORDINALS : 0, &recs, &res);   /* j for output() (-n) on the device */
 	if (rc) { ret = fail("scan"); goto done; }
 	for (i = 0; i < res.n_records; i++) {
 		if (fd == -1 && recs[i].end >= (long long)n) continue;      /* memory mode appends no delimiter (bitap.c:310-314) */
+		if (COUNT && !FILENAMEONLY) { num_of_matched++; continue; } /* (memory mode: the count leaves that last record out too) */
 		if (FILENAMEONLY && (NEW_FILE || !POST_FILTER)) {       /* bitap.c:184-210 */
 			num_of_matched++;
 			if (agrep_finalfp != NULL) fprintf(agrep_finalfp, "%s\n", CurrentFileName);
@@ -242,7 +256,7 @@ int asearch1(char old_D_pat[], int Text, unsigned D)
 int sgrep(unsigned char *in_pat, int in_m, int fd, int D, int samepattern)
 {
 	agb_options o; agb_pattern *p = NULL; agb_result res; agb_record *recs = NULL;
-	char err[256], pat[1024], delim[64]; unsigned char *hb; size_t n = 0, cap, i; int rc, ret = 0, L;
+	char err[256], pat[1024], delim[64]; unsigned char *hb; size_t n = 0, i; int rc, ret = 0, L;
 	unsigned char dpat[2 * AGB_MAXDELIM + 2];
 	(void)samepattern;
 	memset(&o, 0, sizeof o);
@@ -275,14 +289,15 @@ int sgrep(unsigned char *in_pat, int in_m, int fd, int D, int samepattern)
 		} else num_of_matched += (int)res.n_matched;
 		goto done;
 	}
-	cap = n / 2 + 16;
-	recs = (agb_record *)malloc(cap * sizeof *recs);
-	if (!recs) { ret = -1; errno = AGREP_ERROR; goto done; }
-	rc = agb_scan_host(p, hb + 1, n, AGB_WANT_RECORDS, recs, cap, &res);
+	rc = scan_records(p, hb + 1, n, 0, &recs, &res);
 	if (rc) { ret = fail("scan"); goto done; }
 	for (i = 0; i < res.n_records; i++) {
-		/* bm() prints [curtextbegin, curtextend): the line and its trailing newline (sgrep.c:775-789, 916) */
-		long long b = recs[i].begin < 0 ? 0 : recs[i].begin + L, e = recs[i].end + L;
+		/* bm() prints [curtextbegin, curtextend): the line and its trailing newline (sgrep.c:775-789, 916); with a user
+		 * delimiter the record together with the delimiter in FRONT of it, or behind it under -t
+		 * (backward_/forward_delimiter(), delim.c:52-117) */
+		const int tail = !DELIMITER || OUTTAIL;
+		long long b = recs[i].begin < 0 ? 0 : (tail && !(DELIMITER && i == 0 && recs[i].begin == 0 && !(n >= (size_t)L && memcmp(hb + 1, dpat, (size_t)L) == 0)) ? recs[i].begin + L : recs[i].begin);
+		long long e = tail ? recs[i].end + L : recs[i].end;
 		if ((size_t)e > n) e = (long long)n;
 		if (!INVERSE) num_of_matched++;
 		if (agrep_finalfp != NULL) {

@@ -203,12 +203,14 @@ static int add_pattern(build_t *b, const unsigned char *s, int n, const agb_opti
 	return 0;
 }
 
-/* the -i table of bitap.c:171: CP[ISO-8859-1].lower_1 (agrep.c:2769-2792, codepage.c:399-533), stated as
- * identity + ASCII folding + the 32 high-half entries the reference's table holds */
+/* the -i table of bitap.c:171 as the reference leaves it: CP[ISO-8859-1].lower_1 (agrep.c:2769-2792,
+ * codepage.c:399-533) with every byte that serves as a metasymbol put back to itself (agrep.c:2835-2848; in this
+ * codepage that undoes the lower_1 entries of 0x83, 0x8f and 0x99), stated as identity + ASCII folding + the 29
+ * high-half entries that remain */
 void agbi_lut_lower1(unsigned char lut[256])
 {
 	static const unsigned char hi[] = {
-		0x80,0x87, 0x83,0x66, 0x8a,0x9a, 0x8c,0x9c, 0x8e,0x9e, 0x8f,0x86, 0x90,0x82, 0x92,0x91, 0x99,0x94,
+		0x80,0x87, 0x8a,0x9a, 0x8c,0x9c, 0x8e,0x9e, 0x90,0x82, 0x92,0x91,
 		0xc1,0xe1, 0xc3,0xe3, 0xc4,0xe4, 0xc5,0xe5, 0xc7,0xe7, 0xc8,0xe8, 0xc9,0xe9, 0xca,0xea, 0xcc,0xec,
 		0xcd,0xed, 0xce,0xee, 0xcf,0xef, 0xd1,0xf1, 0xd2,0xf2, 0xd3,0xf3, 0xd4,0xf4, 0xd5,0xf5, 0xd6,0xf6,
 		0xd8,0xf8, 0xda,0xfa, 0xdc,0xfc, 0xdd,0xfd, 0xde,0xfe };
@@ -468,7 +470,7 @@ int agbi_build(const char *pattern, const agb_options *o, agb_desc *d, char *err
 	simple = simple_pattern(s, m, o->k, &notsgrep);
 	sg = simple && !o->bestmatch && !(o->nocase && o->k > 0) && !jump && !o->ins_free && !o->linenum
 	     && !(o->wordbound && o->k > 0) && !(o->wholeline && o->k > 0) && !notsgrep;
-	if (sg && o->k == 0 && !o->wholeline && !o->delim) d->engine = AGB_ENGINE_SGREP_BM;
+	if (sg && o->k == 0 && !o->wholeline) d->engine = AGB_ENGINE_SGREP_BM;   /* also under -d: checksg() does not look at the delimiter */
 	else if (o->k > 0 && jump) d->engine = AGB_ENGINE_ASEARCH1;
 	else if (o->k > 4) d->engine = AGB_ENGINE_ASEARCH0;
 	else if (o->k > 0) d->engine = AGB_ENGINE_ASEARCH;     /* also simple k>0 literals: the reference's sgrep filters are lossy */

@@ -13,10 +13,10 @@
  *   (b) every record whose re-fed byte lies inside the chunk is ours.
  * done_until (dense form) remembers how far this thread's previous chunk already got.
  * Returns the number of reported records; writes them at out_pos.. when write is set. */
-template <typename T, int NR, bool COSTS>
-__device__ __forceinline__ uint32_t chunk_records(const RecParams &P, const DevConsts<T> &C, RecShared<T, NR> &SH, Reader &R,
+template <typename T, int NR, bool COSTS, typename RD>
+__device__ __forceinline__ uint32_t chunk_records(const RecParams &P, const DevConsts<T> &C, RecShared<T, NR> &SH, RD &R,
                                                  const int64_t c, int64_t &done_until, const bool write, const uint64_t out_pos, const bool hist,
-                                                 agb_record *first_out = nullptr)
+                                                 agb_record *first_out = nullptr, const int64_t prev_flagged = -2)
 {
 	const int L = C.L;
 	const int64_t n = (int64_t)P.n, lo = c * 16, hi = lo + 15;
@@ -30,8 +30,9 @@ __device__ __forceinline__ uint32_t chunk_records(const RecParams &P, const DevC
 		if (c == 0) { s = 0; found = true; }
 		for (int64_t cc = c - 1; !found; cc--) {
 			if (cc < 0) { s = 0; found = true; break; }
-			uint32_t pw = P.bitmap ? P.bitmap[cc >> 5] : 0xffffffffu;
-			if (pw >> (cc & 31) & 1u) break;                  /* an earlier flagged chunk meets that record: not ours */
+			/* an earlier flagged chunk meets that record: not ours (list form: the flagged chunk before c is known) */
+			if (prev_flagged != -2) { if (cc == prev_flagged) break; }
+			else { const uint32_t pw = P.bitmap ? P.bitmap[cc >> 5] : 0xffffffffu; if (pw >> (cc & 31) & 1u) break; }
 			for (int64_t q = cc * 16 + 15; q >= cc * 16; q--)
 				if (delim_ends_at(R, q, SH.delim, L, C.kind)) { s = q + 1; found = true; break; }
 		}
@@ -356,33 +357,59 @@ k_records_dense(const RecParams P)
 }
 
 /* list form: one thread per surviving chunk of the ordered candidate list (all lanes busy however sparse the
- * survivors are).  Count launch: per-candidate counts; emit launch: writes at the scanned offsets. */
+ * survivors are).  Count launch: per-candidate counts; emit launch: writes at the scanned offsets.  The list length
+ * is read from the device (totals[12]); the grid strides over it.
+ * A candidate's record lies around its chunk: the thread loads LIST_GB groups before it and LIST_GA after it in one go
+ * (independent 16-byte loads: one memory round trip instead of one per group met) into its strip of shared memory and
+ * reads from there; a record that leaves the strip continues on the slow path.  The record belongs to the first flagged
+ * chunk that meets it: with the list in hand that is "the backward search for the record start stops at the candidate
+ * before this one". */
+#define LIST_GB 5
+#define LIST_GA 7
+#define LIST_NG (LIST_GB + 1 + LIST_GA)
+#define LIST_STRIDE (LIST_NG * 4 + 1)                   /* words; odd: the lanes of a warp hit different banks */
+#define LIST_SMEM (REC_THREADS * LIST_STRIDE * 4)
 template <typename T, int NR, bool COSTS>
 __global__ void __launch_bounds__(REC_THREADS)
 k_records_list(const RecParams P)
 {
+	extern __shared__ __align__(16) uint32_t s_win[];
 	__shared__ RecShared<T, NR> SH;
 	DevConsts<T> C;
 	shared_init<T, NR>(SH, C, P.desc, REC_THREADS);
 	unsigned long long ncand = P.totals[12];
 	if (ncand > P.cand_cap) ncand = P.cand_cap;
-	const uint64_t i = (uint64_t)blockIdx.x * REC_THREADS + threadIdx.x;
+	uint32_t *strip = s_win + threadIdx.x * LIST_STRIDE;
+	const int64_t n_groups = (int64_t)P.n_chunks;          /* 16-byte groups that may be read */
 	uint32_t cnt = 0;
-	if (i < ncand) {
+	for (uint64_t i = (uint64_t)blockIdx.x * REC_THREADS + threadIdx.x; i < ncand; i += (uint64_t)gridDim.x * REC_THREADS) {
 		if (P.emit) {
 			/* emit launch: 0 records -> nothing; exactly 1 -> the count launch kept it; more (rare) -> walk again */
 			const uint32_t c0 = P.tile_counts[i];
 			if (c0 == 1) { const uint64_t at = P.tile_offsets[i]; if (at < P.capacity) P.records[at] = P.cand_first[i]; }
-			else if (c0 > 1) {
-				Reader R; R.init(P.text, P.n, SH.delim, C.L);
-				int64_t done_until = INT64_MIN;
-				chunk_records<T, NR, COSTS>(P, C, SH, R, (int64_t)P.cand[i], done_until, true, P.tile_offsets[i], false);
-			}
-		} else {
-			Reader R; R.init(P.text, P.n, SH.delim, C.L);
-			int64_t done_until = INT64_MIN;
-			cnt = chunk_records<T, NR, COSTS>(P, C, SH, R, (int64_t)P.cand[i], done_until, false, 0, true, P.cand_first ? &P.cand_first[i] : nullptr);
-			P.tile_counts[i] = cnt;
+			if (c0 <= 1) continue;
+		}
+		const int64_t c = (int64_t)P.cand[i], prev = i ? (int64_t)P.cand[i - 1] : -1;
+		WindowReader R; R.init(P.text, P.n, SH.delim, C.L);
+		{
+			int64_t g0 = c - LIST_GB, g1 = c + 1 + LIST_GA;
+			if (g0 < 0) g0 = 0;
+			if (g1 > n_groups) g1 = n_groups;
+			uint4 v[LIST_NG];
+#pragma unroll
+			for (int gi = 0; gi < LIST_NG; gi++) if (g0 + gi < g1) v[gi] = __ldg(reinterpret_cast<const uint4 *>(P.text) + g0 + gi);
+#pragma unroll
+			for (int gi = 0; gi < LIST_NG; gi++) if (g0 + gi < g1) { strip[gi * 4] = v[gi].x; strip[gi * 4 + 1] = v[gi].y; strip[gi * 4 + 2] = v[gi].z; strip[gi * 4 + 3] = v[gi].w; }
+			int64_t hi = g1 * 16;
+			if (hi > (int64_t)P.n) hi = (int64_t)P.n;          /* only bytes of the text (the slow path knows the virtual and appended ones) */
+			R.sm = reinterpret_cast<const uint8_t *>(strip); R.lo = g0 * 16; R.len = (uint32_t)(hi - g0 * 16);
+		}
+		int64_t done_until = INT64_MIN;
+		if (P.emit) chunk_records<T, NR, COSTS>(P, C, SH, R, c, done_until, true, P.tile_offsets[i], false, nullptr, prev);
+		else {
+			const uint32_t c1 = chunk_records<T, NR, COSTS>(P, C, SH, R, c, done_until, false, 0, true, P.cand_first ? &P.cand_first[i] : nullptr, prev);
+			P.tile_counts[i] = c1;
+			cnt += c1;
 		}
 	}
 	if (!P.emit) {
@@ -460,15 +487,15 @@ template <typename T, bool COSTS>
 static int launch_records_list_t(int nrows, const RecParams &P, unsigned grid, cudaStream_t st)
 {
 	switch (nrows) {
-	case 1: k_records_list<T, 1, COSTS><<<grid, REC_THREADS, 0, st>>>(P); break;
-	case 2: k_records_list<T, 2, COSTS><<<grid, REC_THREADS, 0, st>>>(P); break;
-	case 3: k_records_list<T, 3, COSTS><<<grid, REC_THREADS, 0, st>>>(P); break;
-	case 4: k_records_list<T, 4, COSTS><<<grid, REC_THREADS, 0, st>>>(P); break;
-	case 5: k_records_list<T, 5, COSTS><<<grid, REC_THREADS, 0, st>>>(P); break;
-	case 6: k_records_list<T, 6, COSTS><<<grid, REC_THREADS, 0, st>>>(P); break;
-	case 7: k_records_list<T, 7, COSTS><<<grid, REC_THREADS, 0, st>>>(P); break;
-	case 8: k_records_list<T, 8, COSTS><<<grid, REC_THREADS, 0, st>>>(P); break;
-	case 9: k_records_list<T, 9, COSTS><<<grid, REC_THREADS, 0, st>>>(P); break;
+	case 1: k_records_list<T, 1, COSTS><<<grid, REC_THREADS, LIST_SMEM, st>>>(P); break;
+	case 2: k_records_list<T, 2, COSTS><<<grid, REC_THREADS, LIST_SMEM, st>>>(P); break;
+	case 3: k_records_list<T, 3, COSTS><<<grid, REC_THREADS, LIST_SMEM, st>>>(P); break;
+	case 4: k_records_list<T, 4, COSTS><<<grid, REC_THREADS, LIST_SMEM, st>>>(P); break;
+	case 5: k_records_list<T, 5, COSTS><<<grid, REC_THREADS, LIST_SMEM, st>>>(P); break;
+	case 6: k_records_list<T, 6, COSTS><<<grid, REC_THREADS, LIST_SMEM, st>>>(P); break;
+	case 7: k_records_list<T, 7, COSTS><<<grid, REC_THREADS, LIST_SMEM, st>>>(P); break;
+	case 8: k_records_list<T, 8, COSTS><<<grid, REC_THREADS, LIST_SMEM, st>>>(P); break;
+	case 9: k_records_list<T, 9, COSTS><<<grid, REC_THREADS, LIST_SMEM, st>>>(P); break;
 	default: return -1;
 	}
 	g_launches++;

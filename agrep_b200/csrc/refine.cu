@@ -1,261 +1,67 @@
 /* agrep_b200/csrc/refine.cu -- stage 1.5: local verification of anchor hits */
-#include "automaton.cuh"
+#include "scan_internal.cuh"
 
 /* ================================================================================================
  * stage 1.5: local verification of anchor hits
  *
  * Stage 1 passes every chunk in which an anchor starts; for a pattern made of common words that is a few
- * percent of all chunks, almost none of which belong to a match.  A match that uses the anchor occurrence at
- * text offset t aligns the pat_len pattern positions to text inside [t - off - k, t + pat_len - off + k), so
- * running the SAME recurrence over just that window (all rows started at Init[0], whose separator bit is the
- * always-on start state; no record logic, which can only remove bits) decides whether the hit can matter.
- * Chunks none of whose hits survive lose their bitmap bit.  A warp first compacts the flagged chunks of its
- * 32 bitmap words into a queue, so all lanes verify; each lane stages the few 16-byte groups around its chunk
- * in shared memory and the lanes walk their windows in lockstep (same length for everyone).
+ * percent of all chunks (4.5 % for `because each`), 99 % of which belong to no match.  A match that uses the
+ * anchor occurrence at text offset t aligns the pat_len pattern positions to text inside
+ * [t - off - k, t + pat_len - off + k): only that window has to be looked at.  Three steps, each a necessary
+ * condition for the next, each run by full warps (32 candidates at a time, whatever their density in the text):
+ *
+ *   detect  which windows of the flagged chunk start an anchor -> the pattern starts p0 = t - off (stage 1's
+ *           polynomial again: the bitmap only says "somewhere in these 16 bytes")
+ *   count   (T1) with at most k errors at most k pattern positions stay unmatched, and a matched position sits on a
+ *           diagonal within +-k of its own: the literal positions whose byte shows up nowhere in its 2k+1 band
+ *           are counted with byte-parallel compares on the window held in registers (no table lookups, no
+ *           recurrence); more than k of them -> no match can use this anchor hit.  Removes 87 % of the hits of
+ *           the benchmark pattern at a quarter of the cost of the recurrence
+ *   walk    the SAME recurrence as the record stage over just the window (all rows started at Init[0], whose
+ *           separator bit is the always-on start state; no record logic, which can only remove bits)
+ *
+ * A chunk one of whose windows passes the walk gets its bit in the survivor bitmap (a second bitmap: stage 1's
+ * is only read); the record stage then runs the reference's loop on the records those chunks meet -- this
+ * stage only ever removes work, it decides nothing.
+ *
+ * A warp owns a contiguous range of bitmap words.  Flagged chunks go through a ring in shared memory, 32 at a
+ * time; the text around a batch (3..8 sixteen-byte groups per lane) is loaded one batch ahead into registers and
+ * stored to the lane's strip of shared memory (odd stride: no bank conflicts) while the next batch's loads are
+ * in flight.  detect and count run back to back on the first pattern start of every chunk; the few chunks with a
+ * second, different start and the starts that passed the count wait in two more rings until 32 of them are
+ * there (partial batches only at the very end of the range).  The warp also counts the survivor bits it sets:
+ * the per-warp counts are what the compaction into the ordered candidate list scans (k_compact_ranges).
  * ============================================================================================== */
 
-/* the recurrence over one window: rows started at Init[0]; the end bits of the last row are sticky (Init1 holds
- * them, maskgen.c:232), so looking at it after the walk is enough.  Called by all lanes together. */
-template <typename T, int NR, bool COSTS>
-__device__ __forceinline__ bool window_passes(const uint8_t *bytes, const bool run, const int wlen, const T init0,
-                                              const T *mask, const DevConsts<T> &C)
-{
-	T S[NR];
-#pragma unroll
-	for (int r = 0; r < NR; r++) S[r] = init0;
-	for (int q = 0; q < wlen; q++) {
-		const int c = run ? bytes[q] : 0;
-		rows_step<T, NR, COSTS>(S, mask[c], C);
-	}
-	return run && (S[NR - 1] & C.endpos) != 0;
-}
+#define REFINE_MAXG  8
+/* refine_u32a.cu, refine_u32b.cu, refine_u64.cu, refine_costs.cu: the kernel's instantiations */
+int refine_launch_u32a(int nrows, const RefineParams &P, unsigned &grid, cudaStream_t st);
+int refine_launch_u32b(int nrows, const RefineParams &P, unsigned &grid, cudaStream_t st);
+int refine_launch_u64(int nrows, const RefineParams &P, unsigned &grid, cudaStream_t st);
+int refine_launch_costs(bool narrow, int nrows, const RefineParams &P, unsigned &grid, cudaStream_t st);
 
-/* which of the 16 windows of a chunk start an anchor: bit (32 + s - off_a) per hit, i.e. the distinct WINDOW STARTS
- * of the pattern around this chunk (two anchors of one occurrence, "beca" and "use " inside "because ", coincide).
- * POLY: stage 1's polynomial finds the (rare) windows worth comparing with IMADs on the otherwise idle FMA pipe. */
-template <int NA, bool POLY>
-__device__ __forceinline__ uint64_t window_starts(const uint32_t *cw, const RefineParams &P)
-{
-	const uint32_t x0 = cw[0] | P.fold, x1 = cw[1] | P.fold, x2 = cw[2] | P.fold, x3 = cw[3] | P.fold, x4 = cw[4] | P.fold;
-	uint32_t wv[16];
-	wv[0] = x0; wv[1] = __funnelshift_r(x0, x1, 8); wv[2] = __funnelshift_r(x0, x1, 16); wv[3] = __funnelshift_r(x0, x1, 24);
-	wv[4] = x1; wv[5] = __funnelshift_r(x1, x2, 8); wv[6] = __funnelshift_r(x1, x2, 16); wv[7] = __funnelshift_r(x1, x2, 24);
-	wv[8] = x2; wv[9] = __funnelshift_r(x2, x3, 8); wv[10] = __funnelshift_r(x2, x3, 16); wv[11] = __funnelshift_r(x2, x3, 24);
-	wv[12] = x3; wv[13] = __funnelshift_r(x3, x4, 8); wv[14] = __funnelshift_r(x3, x4, 16); wv[15] = __funnelshift_r(x3, x4, 24);
-	uint64_t starts = 0;
-	if (POLY) {
-		uint32_t zm = 0;
-#pragma unroll
-		for (int s16 = 0; s16 < 16; s16++) {
-			uint32_t r = wv[s16] * P.one + P.coef[NA - 1];
-#pragma unroll
-			for (int i = NA - 2; i >= 0; i--) r = r * wv[s16] + P.coef[i];
-			if (r * P.scale == 0) zm |= 1u << s16;
-		}
-		for (; zm; zm &= zm - 1) {                             /* usually one bit */
-			const int s16 = __ffs(zm) - 1;
-			const uint32_t lo = cw[s16 >> 2] | P.fold, hi = cw[(s16 >> 2) + 1] | P.fold;     /* rebuilt: wv[] stays in registers */
-			const uint32_t wsel = __funnelshift_r(lo, hi, (s16 & 3) * 8) & P.amask;
-#pragma unroll
-			for (int a = 0; a < NA; a++) if (wsel == P.anchor[a]) starts |= 1ull << (32 + s16 - P.off[a]);
-		}
-	} else {
-#pragma unroll
-		for (int a = 0; a < NA; a++) {
-			const uint32_t A = P.anchor[a];
-			uint32_t m = 0;
-#pragma unroll
-			for (int s16 = 0; s16 < 16; s16++) if ((wv[s16] & P.amask) == A) m |= 1u << s16;
-			starts |= (uint64_t)m << (32 - P.off[a]);              /* off <= 31: refine_geometry() */
-		}
-	}
-	return starts;
-}
-
-template <bool POLY>
-__device__ __forceinline__ uint64_t window_starts_na(const uint32_t *cw, const RefineParams &P)
-{
-	switch (P.na) {
-	case 1: return window_starts<1, POLY>(cw, P);  case 2: return window_starts<2, POLY>(cw, P);
-	case 3: return window_starts<3, POLY>(cw, P);  case 4: return window_starts<4, POLY>(cw, P);
-	case 5: return window_starts<5, POLY>(cw, P);  case 6: return window_starts<6, POLY>(cw, P);
-	case 7: return window_starts<7, POLY>(cw, P);  case 8: return window_starts<8, POLY>(cw, P);
-	default: return window_starts<9, POLY>(cw, P);
-	}
-}
-
-/* Streaming form: every warp owns a contiguous range of bitmap words.  It appends the flagged chunks of 32 words at
- * a time to a ring and, whenever 32 are waiting, judges them together: stage the 16-byte groups around the chunk
- * in shared memory, find the window starts, walk the first window; a chunk whose first window fails loses its bit
- * at once (atomicAnd on the bitmap), its other windows (3 % of the chunks have any) go to a second ring and are
- * judged 32 at a time later -- a pass sets the bit again (atomicOr; same warp, program order).  Rings are only
- * flushed partially at the very end of the warp's range, so the lanes stay full. */
-#define REFINE_RING  1088         /* >= 31 left over + 1024 new per refill */
-
-/* take up to 32 chunks off the ring and start loading the text around them (NGC x 16 bytes per lane, in registers) */
-template <int NGC>
-__device__ __forceinline__ void refine_pop(const RefineParams &P, const uint32_t *ring, uint32_t &head, uint32_t &count, uint32_t lane,
-                                           uint64_t chunk0, uint64_t &chunk, bool &keep, uint4 (&nx)[NGC])
-{
-	const uint32_t m = count < 32 ? count : 32;
-	const bool active = lane < m;
-	chunk = chunk0 + (active ? ring[head + lane] : 0u);
-	head += m; count -= m;
-	const int64_t base = (int64_t)chunk * 16;
-	/* windows that touch the virtual '\n', the appended delimiter or the end of the buffer are not judged here */
-	keep = !active || (base - P.lo_off < 0 || (uint64_t)(base + P.hi_off + 16) > P.n || chunk + 2 >= P.n_chunks);
-	if (!keep) {
-		const uint4 *src = reinterpret_cast<const uint4 *>(P.text) + ((int64_t)chunk - P.gb);
-#pragma unroll
-		for (int gi = 0; gi < NGC; gi++) if (gi < P.ng) nx[gi] = __ldg(src + gi);
-	}
-}
-
-/* append the flagged chunks of the next 32 bitmap words (one per lane, loaded one group ahead) to the ring */
-__device__ __forceinline__ void refine_refill(const RefineParams &P, uint32_t *ring, uint32_t &head, uint32_t &count, uint32_t lane,
-                                              uint64_t &g, uint64_t g_begin, uint64_t g_end, uint32_t &next_word)
-{
-	const uint32_t word = next_word;
-	if (g + 1 < g_end) { const uint64_t w = (g + 1) * 32 + lane; next_word = (w < P.n_words) ? P.bitmap[w] : 0u; }
-	uint32_t c = __popc(word), pre = c;
-#pragma unroll
-	for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= (uint32_t)o) pre += v; }
-	const uint32_t total = __shfl_sync(0xffffffffu, pre, 31);
-	pre -= c;
-	const uint32_t rel0 = (uint32_t)((g - g_begin) * 1024) + lane * 32;
-	if (head) {   /* the (< 32) entries left over move to the front: the ring is used linearly */
-		const uint32_t v = lane < count ? ring[head + lane] : 0u;
-		__syncwarp();
-		if (lane < count) ring[lane] = v;
-		head = 0;
-	}
-	for (uint32_t b = word; b; b &= b - 1) { ring[count + pre] = rel0 + (uint32_t)(__ffs(b) - 1); pre++; }
-	count += total;
-	g++;
-	__syncwarp();
-}
-
-template <typename T, int NR, bool COSTS, int NGC>
+/* survivor bitmap -> ordered candidate list, by the same warp ranges stage 1.5 used: range_offsets is the
+ * exclusive scan of the per-warp survivor counts */
 __global__ void __launch_bounds__(REFINE_THREADS)
-k_refine(const RefineParams P)
+k_compact_ranges(const uint32_t *bitmap, uint64_t n_words, const uint64_t *range_offsets, uint64_t *list, uint64_t cap)
 {
-	extern __shared__ __align__(16) uint32_t s_stage[];     /* REFINE_THREADS x (ng*4 + 1) words */
-	__shared__ RecShared<T, NR> SH;
-	__shared__ uint32_t s_ring[REFINE_THREADS / 32][REFINE_RING];
-	__shared__ unsigned long long s_defer[REFINE_THREADS / 32][REFINE_DEFER];
-	DevConsts<T> C;
-	shared_init<T, NR>(SH, C, P.desc, REFINE_THREADS);
-	const T init0 = mirror<T>((T)P.desc->init0);
-	const int pat_len = P.desc->pat_len, k = C.k, wlen = pat_len + 2 * k;
-	const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5, lt_mask = (1u << lane) - 1u;
-	const int stride_w = P.ng * 4 + 1;                      /* odd number of words: lanes hit different banks */
-	uint32_t *my_stage = s_stage + threadIdx.x * stride_w;
-	const uint8_t *my_bytes = reinterpret_cast<const uint8_t *>(my_stage);
-	const int ws0 = P.gb * 16 - 32 - k;                     /* window offset in the staged bytes = ws0 + start bit */
-	uint32_t *ring = s_ring[wib];
-	unsigned long long *defer = s_defer[wib];
-#define REFINE_WINDOW(ptr, run) window_passes<T, NR, COSTS>((ptr), (run), wlen, init0, SH.mask, C)
-
-	/* this warp's groups of 32 bitmap words: [g_begin, g_end) */
+	const uint32_t lane = threadIdx.x & 31;
 	const uint64_t warp = ((uint64_t)blockIdx.x * REFINE_THREADS + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * REFINE_THREADS) >> 5;
-	const uint64_t n_groups = (P.n_words + 31) / 32, per = (n_groups + nwarps - 1) / nwarps;
-	const uint64_t g_begin = warp * per, g_end = (g_begin + per < n_groups) ? g_begin + per : n_groups;
-	if (g_begin >= g_end) return;
-	const uint64_t chunk0 = g_begin * 1024;                 /* ring entries are chunk numbers relative to this */
-
-	uint32_t head = 0, count = 0, ndefer = 0;               /* warp-uniform */
-	uint64_t g = g_begin;
-	uint32_t next_word = (g * 32 + lane < P.n_words) ? P.bitmap[g * 32 + lane] : 0u;     /* one group ahead */
-	bool have = false;                                      /* a batch is popped and its text on the way in nx[] */
-	uint64_t chunk = 0; bool keep = true;
-	uint4 nx[NGC];
-	for (;;) {
-		/* ---- 32 deferred windows (or what is left of them at the very end) ---- */
-		if (ndefer >= 32 || (ndefer && !have && count == 0 && g >= g_end)) {
-			const uint32_t m = ndefer < 32 ? ndefer : 32;
-			const bool run = lane < m;
-			const unsigned long long e = run ? defer[ndefer - m + lane] : 0ull;
-			const uint64_t dchunk = chunk0 + (uint32_t)(e >> 6);
-			if (run) {
-				const uint4 *src = reinterpret_cast<const uint4 *>(P.text) + ((int64_t)dchunk - P.gb);
-				for (int gi = 0; gi < P.ng; gi++) {
-					const uint4 v = __ldg(src + gi);
-					my_stage[gi * 4 + 0] = v.x; my_stage[gi * 4 + 1] = v.y; my_stage[gi * 4 + 2] = v.z; my_stage[gi * 4 + 3] = v.w;
-				}
-			}
-			if (REFINE_WINDOW(my_bytes + ws0 + (int)(e & 63ull), run))
-				atomicOr(&P.bitmap[dchunk >> 5], 1u << (dchunk & 31));
-			ndefer -= m;
-			__syncwarp();
-			continue;
-		}
-		if (!have) {
-			while (count < 32 && g < g_end) refine_refill(P, ring, head, count, lane, g, g_begin, g_end, next_word);
-			if (count == 0) break;                              /* range done, rings empty */
-			refine_pop<NGC>(P, ring, head, count, lane, chunk0, chunk, keep, nx);      /* (a partial batch only at the very end) */
-		}
-		/* ---- the batch in nx[]: into shared memory; the next one starts loading while this one is judged ---- */
-		const uint64_t cchunk = chunk; const bool ckeep = keep;
-		if (!ckeep) {
+	const uint64_t n_groups = (n_words + 31) / 32, per = (n_groups + nwarps - 1) / nwarps;
+	const uint64_t g_begin = warp * per < n_groups ? warp * per : n_groups, g_end = (g_begin + per < n_groups) ? g_begin + per : n_groups;
+	uint64_t at = range_offsets[warp];
+	for (uint64_t g = g_begin; g < g_end; g++) {
+		const uint64_t w = g * 32 + lane;
+		const uint32_t word = w < n_words ? bitmap[w] : 0u;
+		if (!__ballot_sync(0xffffffffu, word != 0)) continue;
+		uint32_t c = __popc(word), pre = c;
 #pragma unroll
-			for (int gi = 0; gi < NGC; gi++) if (gi < P.ng) {
-				my_stage[gi * 4 + 0] = nx[gi].x; my_stage[gi * 4 + 1] = nx[gi].y; my_stage[gi * 4 + 2] = nx[gi].z; my_stage[gi * 4 + 3] = nx[gi].w;
-			}
-		}
-		while (count < 32 && g < g_end) refine_refill(P, ring, head, count, lane, g, g_begin, g_end, next_word);
-		have = count != 0;                                      /* fewer than 32 only when the range is exhausted */
-		if (have) refine_pop<NGC>(P, ring, head, count, lane, chunk0, chunk, keep, nx);
-		uint64_t starts = 0;
-		if (!ckeep) starts = P.poly ? window_starts_na<true>(my_stage + P.gb * 4, P) : window_starts_na<false>(my_stage + P.gb * 4, P);
-		bool pass = ckeep;
-		{
-			const bool run = starts != 0;
-			const bool ok = REFINE_WINDOW(my_bytes + ws0 + (run ? __ffsll((long long)starts) - 1 : 32), run);
-			if (!ckeep && !ok) atomicAnd(&P.bitmap[cchunk >> 5], ~(1u << (cchunk & 31)));      /* undecided chunks lose the bit now ... */
-			if (ok) pass = true;
-		}
-		/* ... and get it back if one of their other windows passes later */
-		uint64_t rest = (starts && !pass) ? (starts & (starts - 1)) : 0ull;
-		for (;;) {
-			const uint32_t pend = __ballot_sync(0xffffffffu, rest != 0);
-			if (!pend) break;
-			if (ndefer + __popc(pend) > REFINE_DEFER) break;          /* ring full: see below */
-			if (rest != 0) {
-				defer[ndefer + __popc(pend & lt_mask)] = ((unsigned long long)(uint32_t)(cchunk - chunk0) << 6) | (unsigned long long)(__ffsll((long long)rest) - 1);
-				rest &= rest - 1;
-			}
-			ndefer += __popc(pend);
-		}
-		if (rest != 0) atomicOr(&P.bitmap[cchunk >> 5], 1u << (cchunk & 31));     /* could not be queued: keep (stage 2 is exact) */
-		__syncwarp();
+		for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= (uint32_t)o) pre += v; }
+		const uint32_t total = __shfl_sync(0xffffffffu, pre, 31);
+		uint64_t mine = at + (pre - c);
+		for (uint32_t b = word; b; b &= b - 1) { if (mine < cap) list[mine] = w * 32 + (uint64_t)(__ffs(b) - 1); mine++; }
+		at += total;
 	}
-#undef REFINE_WINDOW
-}
-
-template <typename T, int NR, bool COSTS>
-static void launch_refine_one(const RefineParams &P, unsigned grid, cudaStream_t st)
-{
-	const size_t smem = (size_t)REFINE_THREADS * (P.ng * 4 + 1) * sizeof(uint32_t);
-	if (P.ng <= 4) k_refine<T, NR, COSTS, 4><<<grid, REFINE_THREADS, smem, st>>>(P);
-	else k_refine<T, NR, COSTS, REFINE_MAXG><<<grid, REFINE_THREADS, smem, st>>>(P);
-}
-template <typename T, bool COSTS>
-static int launch_refine_t(int nrows, const RefineParams &P, unsigned grid, cudaStream_t st)
-{
-	switch (nrows) {
-	case 1: launch_refine_one<T, 1, COSTS>(P, grid, st); break;
-	case 2: launch_refine_one<T, 2, COSTS>(P, grid, st); break;
-	case 3: launch_refine_one<T, 3, COSTS>(P, grid, st); break;
-	case 4: launch_refine_one<T, 4, COSTS>(P, grid, st); break;
-	case 5: launch_refine_one<T, 5, COSTS>(P, grid, st); break;
-	case 6: launch_refine_one<T, 6, COSTS>(P, grid, st); break;
-	case 7: launch_refine_one<T, 7, COSTS>(P, grid, st); break;
-	case 8: launch_refine_one<T, 8, COSTS>(P, grid, st); break;
-	case 9: launch_refine_one<T, 9, COSTS>(P, grid, st); break;
-	default: return -1;
-	}
-	g_launches++;
-	return 0;
 }
 
 static bool refine_geometry(const agb_desc &d, RefineParams &P)
@@ -268,17 +74,68 @@ static bool refine_geometry(const agb_desc &d, RefineParams &P)
 	P.gb = (P.lo_off + 15) / 16;
 	P.ng = P.gb + (P.hi_off + 15) / 16;
 	if (P.ng < P.gb + 2) P.ng = P.gb + 2;              /* the chunk itself and the word that follows it */
-	return P.ng <= REFINE_MAXG && max_off <= 31;
+	const int pw = (d.pat_len + 3) / 4, ngc = (d.engine != AGB_ENGINE_ASEARCH1 && d.M <= 31 && pw <= 4) ? 4 : REFINE_MAXG;
+	if (!(P.ng <= ngc && max_off <= 31 && d.pat_len >= 1 && d.pat_len <= 64)) return false;
+	/* which anchor a hit window holds is looked up through a multiplicative hash of its bytes: 32 slots, a multiplier
+	 * that keeps the anchors apart (equal anchors at different offsets, "abab" in "abababab", have no such thing: those
+	 * patterns go to stage 2 unthinned) */
+	uint32_t mul = 0x9E3779B1u;
+	for (int attempt = 0; attempt < 4096; attempt++, mul = mul * 0x2C1B3C6Du + 0x297A2D39u) {
+		int8_t slot[32]; bool ok = true;
+		memset(slot, -1, sizeof slot);
+		mul |= 1u;
+		for (int i = 0; i < d.n_anchors && ok; i++) {
+			const uint32_t h = (d.anchor[i] * mul) >> 27;
+			if (slot[h] >= 0) ok = false; else slot[h] = (int8_t)i;
+		}
+		if (!ok) continue;
+		P.hmul = mul;
+		for (int h = 0; h < 32; h++) P.hoff[h] = slot[h] >= 0 ? (int8_t)d.anchor_off[slot[h]] : 0;
+		return true;
+	}
+	return false;
 }
 
-/* stage 1.5 over the whole bitmap */
-int refine_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, cudaStream_t st)
+/* the count step's view of the pattern, from the Mask[] words alone (so descriptors that come from the drop-in layer
+ * work too): position j of the pattern proper is literal when exactly one byte value below 0x80 reaches it, or two
+ * that differ in the 0x20 bit (then every compare is made under that fold, as stage 1 does); everything else --
+ * classes, '.', the -w / -x wrappers, bytes >= 0x80 -- counts as matched */
+static void refine_t1_setup(const agb_desc &d, RefineParams &P)
+{
+	uint8_t lit[64]; bool is_lit[64]; bool fold = false; int n_lit = 0;
+	for (int j = 0; j < d.pat_len; j++) {
+		const uint64_t bit = 1ull << (d.M - (d.L + 2 + j));
+		int cnt = 0, c0 = -1, c1 = -1;
+		for (int c = 0; c < 256; c++) if (d.mask[c] & bit) { if (cnt == 0) c0 = c; else if (cnt == 1) c1 = c; cnt++; }
+		is_lit[j] = false; lit[j] = 0;
+		if (cnt == 1 && c0 < 0x80) { is_lit[j] = true; lit[j] = (uint8_t)c0; }
+		else if (cnt == 2 && (c0 ^ c1) == 0x20 && c1 < 0x80) { is_lit[j] = true; lit[j] = (uint8_t)(c0 | 0x20); fold = true; }
+		if (is_lit[j]) n_lit++;
+	}
+	P.t1 = 0;
+	if (n_lit <= d.k + 1) return;                        /* the count could never fail */
+	P.t1 = 1; P.t1_fold = fold ? 0x20202020u : 0u;
+	for (int w = 0; w < 16; w++) { P.t1_pat[w] = 0; P.t1_care[w] = 0; }
+	for (int j = 0; j < d.pat_len; j++) if (is_lit[j]) {
+		/* stored as pattern byte XOR'ed against the (folded) text; the compare adds 0x7f to the difference */
+		P.t1_pat[j >> 2] |= (uint32_t)(fold ? (lit[j] | 0x20) : lit[j]) << (8 * (j & 3));
+		P.t1_care[j >> 2] |= 0x80u << (8 * (j & 3));
+	}
+	/* positions that are not literal: their byte of the difference is arbitrary and not looked at (care = 0); make the
+	 * pattern byte 0 there so that the 7-bit sums never carry into the next byte: a 7-bit value + 0x7f stays below 0x100 */
+}
+
+/* stage 1.5 over the whole bitmap: W.bitmap -> W.bitmap2, per-warp survivor counts in W.range_counts.
+ * *ran = false when the pattern has no local window (then stage 2 works from W.bitmap) */
+int refine_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, cudaStream_t st, bool *ran)
 {
 	RefineParams P; memset(&P, 0, sizeof P);
+	*ran = false;
 	if (n == 0 || !refine_geometry(d, P)) return AGB_OK;
 	const uint64_t n_chunks = (n + 15) / 16, n_words = (n_chunks + 31) / 32;
-	P.text = (const uint8_t *)d_text; P.bitmap = W.bitmap; P.n = n; P.n_chunks = n_chunks; P.n_words = n_words; P.desc = W.d_desc;
-	P.fold = d.anchor_fold; P.amask = d.anchor_mask; P.na = d.n_anchors;
+	P.text = (const uint8_t *)d_text; P.bitmap = W.bitmap; P.out = W.bitmap2; P.warp_counts = W.range_counts;
+	P.n = n; P.n_chunks = n_chunks; P.n_words = n_words; P.desc = W.d_desc;
+	P.fold = d.anchor_fold; P.amask = d.anchor_mask; P.na = d.n_anchors; P.k = d.k; P.pat_len = d.pat_len;
 	for (int i = 0; i < d.n_anchors; i++) { P.anchor[i] = d.anchor[i]; P.off[i] = d.anchor_off[i]; }
 	{   /* stage 1's polynomial over the anchors, usable when they are pairwise distinct and pass its false-positive guard */
 		bool distinct = true;
@@ -287,14 +144,35 @@ int refine_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t 
 		for (int i = d.anchor_len; i < 4; i++) P.scale <<= 8;
 		P.poly = (distinct && poly_setup(d.anchor, d.n_anchors, 8 * d.anchor_len, P.coef)) ? 1 : 0;
 	}
-	const uint64_t groups = (n_words + 31) / 32;
-	unsigned grid = (unsigned)std::min<uint64_t>((groups + 3) / 4, (uint64_t)W.sm_count * 16);
-	if (!grid) grid = 1;
+	refine_t1_setup(d, P);
+	unsigned grid = refine_grid(W, n);
+	P.sm_count = W.sm_count;
 	const bool costs = d.engine == AGB_ENGINE_ASEARCH1, narrow = d.M <= 31;
-	int rc = costs ? (narrow ? launch_refine_t<uint32_t, true>(d.nrows, P, grid, st) : launch_refine_t<uint64_t, true>(d.nrows, P, grid, st))
-	               : (narrow ? launch_refine_t<uint32_t, false>(d.nrows, P, grid, st) : launch_refine_t<uint64_t, false>(d.nrows, P, grid, st));
+	int rc = costs ? refine_launch_costs(narrow, d.nrows, P, grid, st)
+	       : !narrow ? refine_launch_u64(d.nrows, P, grid, st)
+	       : d.nrows <= 4 ? refine_launch_u32a(d.nrows, P, grid, st) : refine_launch_u32b(d.nrows, P, grid, st);
 	if (rc) return AGB_ERR_ARG;
+	g_launches++;
 	CUDA_TRY(cudaGetLastError());
+	W.refine_ctas = grid;
+	*ran = true;
 	return AGB_OK;
 }
 
+/* upper bound of the grid of stage 1.5 (the launch trims it to one wave and leaves the result in W.refine_ctas: the
+ * warp ranges of the survivor counts and of k_compact_ranges) */
+unsigned refine_grid(const Workspace &W, uint64_t n)
+{
+	const uint64_t n_chunks = (n + 15) / 16, n_words = (n_chunks + 31) / 32, groups = (n_words + 31) / 32;
+	unsigned grid = (unsigned)std::min<uint64_t>((groups + 3) / 4, (uint64_t)W.sm_count * 16);
+	return grid ? grid : 1;
+}
+
+int compact_ranges_launch(Workspace &W, uint64_t n, cudaStream_t st)
+{
+	const uint64_t n_chunks = (n + 15) / 16, n_words = (n_chunks + 31) / 32;
+	const unsigned grid = W.refine_ctas;
+	k_compact_ranges<<<grid, REFINE_THREADS, 0, st>>>(W.bitmap2, n_words, W.range_offsets, W.cand, W.cand_cap); g_launches++;
+	CUDA_TRY(cudaGetLastError());
+	return AGB_OK;
+}

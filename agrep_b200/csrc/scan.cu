@@ -47,6 +47,8 @@ static int ws_prepare(Workspace &W, uint64_t n)
 		CUDA_TRY(cudaMalloc(&W.totals, 16 * sizeof(unsigned long long)));
 		CUDA_TRY(cudaMallocHost(&W.h_totals, 16 * sizeof(unsigned long long)));
 		CUDA_TRY(cudaMalloc(&W.d_desc, sizeof(agb_desc)));
+		CUDA_TRY(cudaMalloc(&W.range_counts, REFINE_MAX_RANGES * sizeof(uint32_t)));
+		CUDA_TRY(cudaMalloc(&W.range_offsets, REFINE_MAX_RANGES * sizeof(uint64_t)));
 		CUDA_TRY(cudaEventCreate(&W.e0)); CUDA_TRY(cudaEventCreate(&W.e1)); CUDA_TRY(cudaEventCreate(&W.e2));
 		int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
 		CUDA_TRY(cudaDeviceGetAttribute(&W.sm_count, cudaDevAttrMultiProcessorCount, dev));
@@ -55,8 +57,10 @@ static int ws_prepare(Workspace &W, uint64_t n)
 	size_t bb = (size_t)(n_words + FRONT_WORDS_PER_STAGE) * 4;
 	if (bb > W.bitmap_bytes) {
 		if (W.bitmap) cudaFree(W.bitmap);
-		W.bitmap = nullptr; W.bitmap_bytes = 0;
-		CUDA_TRY(cudaMalloc(&W.bitmap, bb)); W.bitmap_bytes = bb;
+		if (W.bitmap2) cudaFree(W.bitmap2);
+		W.bitmap = nullptr; W.bitmap2 = nullptr; W.bitmap_bytes = 0;
+		CUDA_TRY(cudaMalloc(&W.bitmap, bb));
+		CUDA_TRY(cudaMalloc(&W.bitmap2, bb)); W.bitmap_bytes = bb;
 	}
 	if (tiles + 1 > W.tiles) {
 		if (W.tile_counts) cudaFree(W.tile_counts);
@@ -105,20 +109,52 @@ static int ws_upload_desc(Workspace &W, const agb_desc &d, cudaStream_t st)
 	return AGB_OK;
 }
 
+/* the ordered candidate list -> records: count launch (per-candidate counts, the first record of each kept), scan,
+ * emit launch.  The list length lives on the device (totals[12]); every grid here is sized by the list's capacity. */
+static int list_stage(const agb_desc &d, Workspace &W, RecParams &P, bool want_list, cudaStream_t st)
+{
+	P.cand = W.cand; P.cand_cap = W.cand_cap; P.tile_counts = W.cand_counts; P.tile_offsets = W.cand_offsets;
+	P.cand_first = want_list ? W.cand_first : nullptr;
+	const unsigned grid = (unsigned)std::min<uint64_t>((W.cand_cap + REC_THREADS - 1) / REC_THREADS, (uint64_t)W.sm_count * 16);
+	if (launch_records_list(d, P, grid, st)) return AGB_ERR_ARG;
+	CUDA_TRY(cudaGetLastError());
+	if (want_list) {
+		const unsigned nb = (unsigned)((W.cand_cap + SCAN_BLOCK - 1) / SCAN_BLOCK);
+		k_scan_partial<<<nb, 1024, 0, st>>>(W.cand_counts, W.cand_cap, W.scan_sums, W.totals + 12);
+		k_scan_tiles<<<1, 1024, 0, st>>>(W.scan_sums, W.scan_offs, nb, nullptr);
+		k_scan_apply<<<nb, 1024, 0, st>>>(W.cand_counts, W.cand_cap, W.scan_offs, W.cand_offsets, W.totals + 12);
+		g_launches += 3;
+		P.emit = 1;
+		if (launch_records_list(d, P, grid, st)) return AGB_ERR_ARG;
+		CUDA_TRY(cudaGetLastError());
+	}
+	return AGB_OK;
+}
+
 /* stage 2 over the whole text.  After stage 1.5 the survivors are few: they are compacted into an ordered list
  * and each gets its own thread (count launch -> scan -> emit launch).  Otherwise (or if the list would not fit)
- * the dense form walks the bitmap, one thread per word. */
-static int records_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, bool use_front, int want,
+ * the dense form walks the bitmap, one thread per word.
+ * refined: stage 1.5 ran -- the survivors are in W.bitmap2, their per-range counts in W.range_counts, and nothing
+ * here needs the host to know how many there are (the list is sized by W.cand_hint / a fraction of the chunks; the
+ * caller checks totals[12] against W.cand_cap afterwards and comes back with refined_retry set if it was too small). */
+static int records_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, bool use_front, bool refined, int want,
                           int want_level, agb_record *d_records, uint64_t capacity, cudaStream_t st)
 {
 	const uint64_t n_chunks = (n + 15) / 16, n_words = (n_chunks + 31) / 32, tiles = (n_words + REC_THREADS - 1) / REC_THREADS;
 	RecParams P; memset(&P, 0, sizeof P);
-	P.text = (const uint8_t *)d_text; P.bitmap = use_front ? W.bitmap : nullptr;
+	P.text = (const uint8_t *)d_text; P.bitmap = use_front ? (refined ? W.bitmap2 : W.bitmap) : nullptr;
 	P.n = n; P.n_chunks = n_chunks; P.n_words = n_words; P.desc = W.d_desc;
 	P.records = d_records; P.capacity = capacity;
 	P.totals = W.totals; P.emit = 0; P.levels = (want & AGB_WANT_LEVELS) ? 1 : 0; P.want_level = want_level;
 	if (!tiles) return AGB_OK;
 	const bool want_list = (want & AGB_WANT_RECORDS) && capacity;
+	if (use_front && refined) {
+		int rc = ws_cand_reserve(W, std::max<size_t>(W.cand_hint + W.cand_hint / 4, (size_t)(n_chunks / 512) + 65536)); if (rc) return rc;
+		const unsigned ranges = W.refine_ctas * (REFINE_THREADS / 32);
+		k_scan_tiles<<<1, 1024, 0, st>>>(W.range_counts, W.range_offsets, ranges, W.totals + 12); g_launches++;
+		rc = compact_ranges_launch(W, n, st); if (rc) return rc;
+		return list_stage(d, W, P, want_list, st);
+	}
 	if (use_front) {
 		const uint64_t blocks = (n_words + COMPACT_THREADS * COMPACT_WPT - 1) / (COMPACT_THREADS * COMPACT_WPT);
 		k_compact_count<<<(unsigned)blocks, COMPACT_THREADS, 0, st>>>(W.bitmap, n_words, W.tile_counts, W.totals); g_launches++;
@@ -135,25 +171,7 @@ static int records_launch(const agb_desc &d, Workspace &W, const void *d_text, u
 		} else if (ws_cand_reserve(W, (size_t)ncand) == AGB_OK) {
 			if (ncand == 0) return AGB_OK;
 			k_compact_write<<<(unsigned)blocks, COMPACT_THREADS, 0, st>>>(W.bitmap, n_words, W.tile_offsets, W.cand, W.cand_cap); g_launches++;
-			P.cand = W.cand; P.cand_cap = W.cand_cap; P.tile_counts = W.cand_counts; P.tile_offsets = W.cand_offsets;
-			P.cand_first = want_list ? W.cand_first : nullptr;
-			const unsigned grid = (unsigned)((ncand + REC_THREADS - 1) / REC_THREADS);
-			if (launch_records_list(d, P, grid, st)) return AGB_ERR_ARG;
-			CUDA_TRY(cudaGetLastError());
-			if (want_list) {
-				if (ncand <= 4 * SCAN_BLOCK) { k_scan_tiles<<<1, 1024, 0, st>>>(W.cand_counts, W.cand_offsets, ncand, nullptr); g_launches++; }
-				else {
-					const unsigned nb = (unsigned)((ncand + SCAN_BLOCK - 1) / SCAN_BLOCK);
-					k_scan_partial<<<nb, 1024, 0, st>>>(W.cand_counts, ncand, W.scan_sums);
-					k_scan_tiles<<<1, 1024, 0, st>>>(W.scan_sums, W.scan_offs, nb, nullptr);
-					k_scan_apply<<<nb, 1024, 0, st>>>(W.cand_counts, ncand, W.scan_offs, W.cand_offsets);
-					g_launches += 3;
-				}
-				P.emit = 1;
-				if (launch_records_list(d, P, grid, st)) return AGB_ERR_ARG;
-				CUDA_TRY(cudaGetLastError());
-			}
-			return AGB_OK;
+			return list_stage(d, W, P, want_list, st);
 		}
 		else CUDA_TRY(cudaMemsetAsync(W.totals + 1, 0, sizeof(unsigned long long), st));   /* no scratch for a list: bitmap form below recounts totals[1] */
 	}
@@ -190,14 +208,15 @@ static int records_launch(const agb_desc &d, Workspace &W, const void *d_text, u
  * pattern of common words flags 8 % of the chunks and keeps none), so the decision waits for the list length. */
 static bool refine_cannot_thin(const agb_desc &d) { return d.k == 0 && d.n_anchors == 1 && d.pat_len <= d.anchor_len; }
 
-static int fetch_result(Workspace &W, int want, uint64_t capacity, cudaStream_t st, agb_result *res)
+static int fetch_result(Workspace &W, int want, uint64_t capacity, bool refined, cudaStream_t st, agb_result *res)
 {
 	CUDA_TRY(cudaMemcpyAsync(W.h_totals, W.totals, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(cudaStreamSynchronize(st));
 	res->n_matched = W.h_totals[0];
-	res->n_flagged = W.h_totals[1];
+	res->n_flagged = refined ? W.h_totals[12] : W.h_totals[1];
 	for (int i = 0; i <= AGB_MAXERR; i++) res->level_hist[i] = W.h_totals[2 + i];
 	res->n_records = (want & AGB_WANT_RECORDS) ? std::min<uint64_t>(res->n_matched, capacity) : 0;
+	res->truncated = ((want & AGB_WANT_RECORDS) && res->n_matched > capacity) ? 1 : 0;
 	res->n_closes = (want & AGB_WANT_ORDINALS) ? W.h_totals[13] + (uint64_t)W.ord_virt : 0;
 	return AGB_OK;
 }
@@ -209,6 +228,34 @@ static int ordinals_prepare_blocks(const agb_desc &d, Workspace &W, uint64_t n, 
 	int rc = ordinals_reserve(d, W, n); if (rc) return rc;
 	const uint64_t n_words = ((n + 15) / 16 + 31) / 32;
 	if (W.ord_blocks_cap > n_words) CUDA_TRY(cudaMemsetAsync(W.ord_blocks + n_words, 0, (W.ord_blocks_cap - n_words) * sizeof(uint16_t), st));
+	return AGB_OK;
+}
+
+/* everything after stage 1, on one stream: stage 1.5, the record stage, the ordinals, the result read-back (the one
+ * host synchronisation of a scan).  The candidate list of the list form is sized without asking the device how many
+ * survivors there are; should it turn out too small (totals[12] > capacity, seen in the read-back) the record stage
+ * alone is run again with the right size -- or in its every-byte form when the survivors are dense. */
+static int stages_after_front(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, bool use_front, bool count_in_front,
+                              int want, int want_level, agb_record *d_records, uint64_t capacity, cudaStream_t st, agb_result *res)
+{
+	int rc;
+	const uint64_t n_chunks = (n + 15) / 16;
+	if (use_front && refine_cannot_thin(d)) { bool dense = false; rc = front_is_dense(W, n, st, &dense); if (rc) return rc; if (dense) use_front = false; }
+	bool refined = false;
+	if (use_front) { rc = refine_launch(d, W, d_text, n, st, &refined); if (rc) return rc; }
+	for (int attempt = 0; ; attempt++) {
+		rc = records_launch(d, W, d_text, n, use_front, refined, want, want_level, d_records, capacity, st); if (rc) return rc;
+		if (want & AGB_WANT_ORDINALS) { rc = ordinals_launch(d, W, d_text, n, (want & AGB_WANT_RECORDS) ? d_records : nullptr, capacity, st, count_in_front); if (rc) return rc; }
+		CUDA_TRY(cudaEventRecord(W.e2, st));
+		rc = fetch_result(W, want, capacity, use_front && refined, st, res); if (rc) return rc;
+		if (!(use_front && refined)) break;
+		const uint64_t ncand = W.h_totals[12];
+		W.cand_hint = (size_t)ncand;
+		if (ncand <= W.cand_cap || attempt) break;
+		/* the list was too small: again, with the size known now (sparse) or over every byte (dense) */
+		if (ncand > n_chunks / 20 + 1024) { use_front = false; refined = false; }
+		CUDA_TRY(cudaMemsetAsync(W.totals, 0, 12 * sizeof(unsigned long long), st));
+	}
 	return AGB_OK;
 }
 
@@ -233,12 +280,7 @@ static int scan_device_impl(const agb_desc &d, const void *d_text, uint64_t n, i
 	if (count_in_front) { rc = ordinals_prepare_blocks(d, W, n, st); if (rc) return rc; }
 	if (use_front) { rc = front_launch(d, W, d_text, n, 0, ~0ull, false, st, count_in_front); if (rc) return rc; }
 	CUDA_TRY(cudaEventRecord(W.e1, st));
-	if (use_front && refine_cannot_thin(d)) { bool dense = false; rc = front_is_dense(W, n, st, &dense); if (rc) return rc; if (dense) use_front = false; }
-	if (use_front) { rc = refine_launch(d, W, d_text, n, st); if (rc) return rc; }
-	rc = records_launch(d, W, d_text, n, use_front, want, want_level, d_records, capacity, st); if (rc) return rc;
-	if (want & AGB_WANT_ORDINALS) { rc = ordinals_launch(d, W, d_text, n, (want & AGB_WANT_RECORDS) ? d_records : nullptr, capacity, st, count_in_front); if (rc) return rc; }
-	CUDA_TRY(cudaEventRecord(W.e2, st));
-	rc = fetch_result(W, want, capacity, st, res); if (rc) return rc;
+	rc = stages_after_front(d, W, d_text, n, use_front, count_in_front, want, want_level, d_records, capacity, st, res); if (rc) return rc;
 	CUDA_TRY(cudaEventElapsedTime(&res->ms_front, W.e0, W.e1));
 	CUDA_TRY(cudaEventElapsedTime(&res->ms_records, W.e1, W.e2));
 	return AGB_OK;
@@ -340,13 +382,7 @@ static int scan_stream_impl(const agb_desc &d, uint64_t n, const SliceSource &sr
 		if (use_front) { rc = front_launch(d, W, W.h2d_text, n, (n_slices - 1) * words_per_slice, ~0ull, true, W.s_comp, count_in_front); if (rc) return rc; }
 	}
 	CUDA_TRY(cudaEventRecord(W.e1, W.s_comp));
-	bool use_bitmap = use_front;
-	if (use_bitmap && refine_cannot_thin(d)) { bool dense = false; rc = front_is_dense(W, n, W.s_comp, &dense); if (rc) return rc; if (dense) use_bitmap = false; }
-	if (use_bitmap) { rc = refine_launch(d, W, W.h2d_text, n, W.s_comp); if (rc) return rc; }
-	rc = records_launch(d, W, W.h2d_text, n, use_bitmap, want, -1, W.h2d_rec, capacity, W.s_comp); if (rc) return rc;
-	if (want & AGB_WANT_ORDINALS) { rc = ordinals_launch(d, W, W.h2d_text, n, (want & AGB_WANT_RECORDS) ? W.h2d_rec : nullptr, capacity, W.s_comp, count_in_front); if (rc) return rc; }
-	CUDA_TRY(cudaEventRecord(W.e2, W.s_comp));
-	rc = fetch_result(W, want, capacity, W.s_comp, res); if (rc) return rc;
+	rc = stages_after_front(d, W, W.h2d_text, n, use_front, count_in_front, want, -1, W.h2d_rec, capacity, W.s_comp, res); if (rc) return rc;
 	if (res->n_records) {
 		CUDA_TRY(cudaMemcpyAsync(records, W.h2d_rec, res->n_records * sizeof(agb_record), cudaMemcpyDeviceToHost, W.s_comp));
 		CUDA_TRY(cudaStreamSynchronize(W.s_comp));

@@ -54,16 +54,19 @@ struct FrontParams {
 
 /* ---- stage 1.5 ---- */
 #define REFINE_THREADS 128
-#define REFINE_MAXG 8
-#define REFINE_DEFER 96          /* deferred windows per warp */
 struct RefineParams {
-	const uint8_t *text; uint32_t *bitmap; uint64_t n, n_chunks, n_words;
+	const uint8_t *text; const uint32_t *bitmap; uint32_t *out; uint32_t *warp_counts;
+	uint64_t n, n_chunks, n_words;
 	const agb_desc *desc;
-	uint32_t fold, amask; int na;
-	int gb, ng;                  /* groups staged before the chunk, groups staged in total (<= REFINE_MAXG) */
+	uint32_t fold, amask; int na, k, pat_len;
+	int gb, ng;                  /* groups staged before the chunk, groups staged in total */
 	int lo_off, hi_off;          /* the windows of a chunk at byte `base` lie inside [base - lo_off, base + hi_off) */
 	uint32_t anchor[AGB_MAXANCHOR]; int32_t off[AGB_MAXANCHOR];
 	uint32_t coef[AGB_MAXANCHOR]; uint32_t one, scale; int poly;   /* stage 1's polynomial, to spot the candidate windows cheaply */
+	int t1, t1_words;            /* the band count: usable; words of the window [p0 - k, p0 + pat_len + k) */
+	uint32_t t1_fold, t1_pat[16], t1_care[16];   /* literal pattern bytes (little endian words), 0x80 per literal position */
+	uint32_t hmul; int8_t hoff[32];              /* anchor bytes -> off: slot (bytes * hmul) >> 27 */
+	int sm_count;
 };
 
 /* ---- stage 2 ---- */
@@ -119,6 +122,10 @@ struct OrdParams {
 #define STAGE_BUFS  3
 struct Workspace {               /* grow-only device scratch, one per device */
 	uint32_t *bitmap = nullptr; size_t bitmap_bytes = 0;
+	uint32_t *bitmap2 = nullptr;                                    /* stage 1.5: the survivors (same size as bitmap) */
+	uint32_t *range_counts = nullptr; uint64_t *range_offsets = nullptr;   /* per warp range of stage 1.5: survivor counts, their scan */
+	unsigned refine_ctas = 0;                                       /* grid of the last stage 1.5 launch */
+	size_t cand_hint = 0;                                          /* candidates the last scans needed (sizes the list without a host round trip) */
 	uint32_t *tile_counts = nullptr; uint64_t *tile_offsets = nullptr; size_t tiles = 0;
 	uint64_t *cand = nullptr; uint32_t *cand_counts = nullptr; uint64_t *cand_offsets = nullptr; agb_record *cand_first = nullptr; size_t cand_cap = 0;
 	uint32_t *scan_sums = nullptr; uint64_t *scan_offs = nullptr; size_t scan_cap = 0;
@@ -142,7 +149,10 @@ bool front_usable(const agb_desc &d);
 bool poly_setup(const uint32_t *a, int na, int bits, uint32_t *coef);
 int  front_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, uint64_t word_begin, uint64_t word_end, bool slack16, cudaStream_t st, bool count_delims = false);
 /* refine.cu */
-int  refine_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, cudaStream_t st);
+int  refine_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, cudaStream_t st, bool *ran);
+unsigned refine_grid(const Workspace &W, uint64_t n);
+int  compact_ranges_launch(Workspace &W, uint64_t n, cudaStream_t st);
+#define REFINE_MAX_RANGES 16384  /* >= warps of the largest stage 1.5 grid */
 /* records.cu, slices.cu: one launch of the given form (count pass or emit pass, RecParams.emit) */
 int  launch_records(const agb_desc &d, const RecParams &P, unsigned grid, cudaStream_t st);
 int  launch_dense(const agb_desc &d, const RecParams &P, unsigned grid, cudaStream_t st);
@@ -153,8 +163,8 @@ bool slices_usable(const agb_desc &d);
 __global__ void k_compact_count(const uint32_t *bitmap, uint64_t n_words, uint32_t *block_counts, unsigned long long *totals);
 __global__ void k_compact_write(const uint32_t *bitmap, uint64_t n_words, const uint64_t *block_offsets, uint64_t *cand, uint64_t cand_cap);
 __global__ void k_scan_tiles(const uint32_t *counts, uint64_t *offsets, uint64_t n_tiles, unsigned long long *total);
-__global__ void k_scan_partial(const uint32_t *counts, uint64_t n, uint32_t *block_sums);
-__global__ void k_scan_apply(const uint32_t *counts, uint64_t n, const uint64_t *block_offsets, uint64_t *offsets);
+__global__ void k_scan_partial(const uint32_t *counts, uint64_t n, uint32_t *block_sums, const unsigned long long *n_dev);
+__global__ void k_scan_apply(const uint32_t *counts, uint64_t n, const uint64_t *block_offsets, uint64_t *offsets, const unsigned long long *n_dev);
 int  front_is_dense(Workspace &W, uint64_t n, cudaStream_t st, bool *dense);
 int  ordinals_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, agb_record *d_records, uint64_t capacity, cudaStream_t st, bool blocks_counted = false);
 int  ordinals_reserve(const agb_desc &d, Workspace &W, uint64_t n);

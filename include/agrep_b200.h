@@ -112,12 +112,15 @@ enum { AGB_WANT_COUNT = 0, AGB_WANT_RECORDS = 1, AGB_WANT_ORDINALS = 2, AGB_WANT
 
 typedef struct agb_result {
 	uint64_t n_matched;       /* num_of_matched for this text                                 */
-	uint64_t n_records;       /* entries written to records (<= capacity)                     */
+	uint64_t n_records;       /* entries written to records (<= capacity; see truncated)      */
 	uint64_t n_flagged;       /* 16-byte chunks the front-end passed to the record stage      */
 	uint64_t level_hist[AGB_MAXERR + 1];      /* AGB_WANT_LEVELS: records by smallest level   */
 	float    ms_front, ms_records;            /* device time of the two stages (CUDA events)  */
 	uint64_t n_closes;        /* AGB_WANT_ORDINALS: record closes in the whole text, the virtual '\n' included (j at EOF):
 	                             what a following shard adds to its ordinals      */
+	uint32_t truncated;       /* 1: AGB_WANT_RECORDS and n_matched > capacity -- the list holds only the first `capacity`
+	                             records (n_records of them); count again with a list of n_matched entries */
+	uint32_t pad;
 } agb_result;
 
 /* ---- pattern front-end (host; mirrors checksg.c + preproce.c + maskgen.c) ---- */

@@ -15,14 +15,16 @@ enum { HYPHEN = 129, NOCARE = 130, NNLINE = 131, WORDB = 133, LPARENT = 134, RPA
 
 #define FAIL(...) do { if (err && errlen) snprintf(err, errlen, __VA_ARGS__); return -1; } while (0)
 
-/* -i selects CP[ISO-8859-1].lower_1 as LUT (agrep.c:2769-2792; table codepage.c:399-533).
- * Restated as "identity except": ASCII A-Z -> a-z plus the irregular high half observed in the
- * reference's table (pinned by tests/golden/lut_lower1.json, generated from the reference). */
+/* -i selects CP[ISO-8859-1].lower_1 as LUT (agrep.c:2769-2792; table codepage.c:399-533) and then puts every
+ * byte that serves as a metasymbol back to itself (agrep.c:2835-2848: 0x83, 0x8f, 0x99 lose their lower_1 entry).
+ * Restated as "identity except": ASCII A-Z -> a-z plus the irregular high half of the table the reference ends up
+ * with (pinned by tests/golden/lut_lower1.json, generated from the reference, and against the binary itself in
+ * tests/test_oracle_vs_reference.py). */
 void orc_lut_lower1(unsigned char lut[256])
 {
 	static const unsigned char ex[][2] = {
-		{0x80,0x87},{0x83,0x66},{0x8a,0x9a},{0x8c,0x9c},{0x8e,0x9e},{0x8f,0x86},{0x90,0x82},
-		{0x92,0x91},{0x99,0x94},{0xc1,0xe1},{0xc3,0xe3},{0xc4,0xe4},{0xc5,0xe5},{0xc7,0xe7},
+		{0x80,0x87},{0x8a,0x9a},{0x8c,0x9c},{0x8e,0x9e},{0x90,0x82},
+		{0x92,0x91},{0xc1,0xe1},{0xc3,0xe3},{0xc4,0xe4},{0xc5,0xe5},{0xc7,0xe7},
 		{0xc8,0xe8},{0xc9,0xe9},{0xca,0xea},{0xcc,0xec},{0xcd,0xed},{0xce,0xee},{0xcf,0xef},
 		{0xd1,0xf1},{0xd2,0xf2},{0xd3,0xf3},{0xd4,0xf4},{0xd5,0xf5},{0xd6,0xf6},{0xd8,0xf8},
 		{0xda,0xfa},{0xdc,0xfc},{0xdd,0xfd},{0xde,0xfe} };
@@ -247,12 +249,36 @@ int orc_compile(const char *pattern, const orc_opts *o, orc_automaton *a, char *
 		FAIL("k>0 simple patterns use sgrep's lossy filters in the reference (SURVEY 8c); force the automaton with linenum=1");
 	if (a->sgrep) {                                                         /* sgrep.c:289-320 */
 		int i, n = 0;
-		if (o->delim) FAIL("oracle restates sgrep/bm for newline records only");
+		if (o->delim) {
+			/* sgrep keeps its engine under -d (checksg.c:124-138): bm() cuts records with backward_/forward_delimiter()
+			 * (sgrep.c:775-795, delim.c:52-117: plain byte search for the delimiter).  Restated for delimiters that cannot
+			 * overlap themselves or the literal (anything else depends on bm()'s skip order). */
+			unsigned char dl[ORC_MAXDELIM + 2]; int L = 0, b; size_t q, dn = strlen(o->delim);
+			for (q = 0; q < dn; q++) {                      /* delim.c:7-29 preprocess_delimiter() */
+				unsigned char c = (unsigned char)o->delim[q];
+				if (c == '\\' && q + 1 < dn) c = (unsigned char)o->delim[++q];
+				else if (c == '^' || c == '$') c = '\n';
+				if (L >= ORC_MAXDELIM) FAIL("delimiter pattern too long (has > %d chars)", ORC_MAXDELIM);
+				dl[L++] = c;
+			}
+			for (b = 1; b < L; b++) if (memcmp(dl, dl + L - b, (size_t)b) == 0) FAIL("oracle: sgrep -d with a self-overlapping delimiter is not restated");
+			memcpy(a->dpat, dl, (size_t)L); a->L = L;
+		}
 		if (o->inverse) FAIL("sgrep -v: the reference counts MATCHING lines under -c (defect); not restated");
 		if (o->wholeline) FAIL("oracle does not restate sgrep -x (reference defect, SURVEY 8c(8))");
 		for (i = 0; i < m; i++) { if (pat[i] == '\\') i++; if (i < m) a->lit[n++] = pat[i]; }
 		if (n > 20) { /* LONG_EXAC: monkey() instead of bm(); same record semantics */ }
-		a->litlen = n; a->lit_word = o->wordbound; a->engine = 4; a->L = 1; a->dpat[0] = '\n';
+		a->litlen = n; a->lit_word = o->wordbound; a->engine = 4;
+		if (!o->delim) { a->L = 1; a->dpat[0] = '\n'; }
+		else {
+			int q, t;                                       /* the (folded) literal must not hold a delimiter byte */
+			for (q = 0; q < n; q++) for (t = 0; t < a->L; t++) {
+				int x = a->lit[q], y = a->dpat[t];
+				if (ascii_upper(x)) x += 32;
+				if (ascii_upper(y)) y += 32;
+				if (x == y) FAIL("oracle: sgrep -d with delimiter bytes inside the literal is not restated");
+			}
+		}
 		return 0;
 	}
 	if (preprocess(pat, o, dpattern, internal, &plen, a->dpat, &a->L, err, errlen)) return -1;
@@ -407,14 +433,15 @@ static int64_t scan_costs(const orc_automaton *a, const unsigned char *text, uin
  * most once (jump to end of record, :812,889-891). */
 static int64_t scan_bm(const orc_automaton *a, const unsigned char *text, uint64_t n, orc_record *recs, uint64_t cap)
 {
-	uint64_t ls = 0, matched = 0, line = 0; int m = a->litlen;
+	uint64_t rs = 0, matched = 0, recno = 0; int m = a->litlen, L = a->L;
+	int64_t begin = a->user_delim ? 0 : -1;      /* same convention as the automaton path: the delimiter that closed the record before */
 	unsigned char pat[256]; int i;
 	for (i = 0; i < m; i++) pat[i] = (unsigned char)(ascii_upper(a->lit[i]) ? a->lit[i] + 32 : a->lit[i]);
-	while (ls < n) {
-		uint64_t le = ls, p; int hit = 0;
-		while (le < n && text[le] != '\n') le++;
-		line++;
-		for (p = ls; !hit && p + (uint64_t)m <= le; p++) {
+	while (rs < n) {
+		uint64_t re = rs, p; int hit = 0;
+		while (re < n && !(re + (uint64_t)L <= n && memcmp(text + re, a->dpat, (size_t)L) == 0)) re++;   /* forward_delimiter(), delim.c:52-76 */
+		recno++;
+		for (p = rs; !hit && p + (uint64_t)m <= re; p++) {
 			for (i = 0; i < m; i++) { int c = text[p + i]; if (ascii_upper(c)) c += 32; if (c != pat[i]) break; }
 			if (i < m) continue;
 			if (a->lit_word) {
@@ -426,12 +453,12 @@ static int64_t scan_bm(const orc_automaton *a, const unsigned char *text, uint64
 		}
 		if (hit) {
 			if (recs && matched < cap) {
-				/* same record convention as the automaton path: begin at the previous line's '\n' (-1 = the virtual one) */
-				recs[matched].begin = (int64_t)ls - 1; recs[matched].end = (int64_t)le; recs[matched].ordinal = (int64_t)line; recs[matched].level = 0;
+				recs[matched].begin = begin; recs[matched].end = (int64_t)re; recs[matched].ordinal = (int64_t)recno; recs[matched].level = 0;
 			}
 			matched++;
 		}
-		ls = le + 1;
+		begin = (int64_t)re;
+		rs = re + (uint64_t)L;
 	}
 	return (int64_t)matched;
 }

@@ -99,13 +99,14 @@ def main():
     for p in files.values():
         os.unlink(p)
     json.dump(out, open(os.path.join(HERE, "reference_vectors.json"), "w"), indent=1, sort_keys=True)
-    # the -i translation table (CP[ISO-8859-1].lower_1, agrep.c:2769-2792)
+    # the -i translation table as the reference ends up with it: CP[ISO-8859-1].lower_1 (agrep.c:2769-2792), identity
+    # again for every byte that serves as a metasymbol (agrep.c:2835-2848)
     import ctypes
     lib = ctypes.CDLL(REF + "/libagrepref.so")
     class E(ctypes.Structure):
         _fields_ = [("l1", ctypes.c_ubyte), ("l2", ctypes.c_ubyte), ("l3", ctypes.c_ubyte), ("m", ctypes.c_int)]
     CP = ((E * 257) * 3).in_dll(lib, "CP")
-    json.dump([CP[2][i].l1 for i in range(256)], open(os.path.join(HERE, "lut_lower1.json"), "w"))
+    json.dump([CP[2][i].l1 if CP[2][i].m == 0 else i for i in range(256)], open(os.path.join(HERE, "lut_lower1.json"), "w"))
     print("wrote", len(out["scan"]), "scan cases,", len(out["dump"]), "dumps")
 
 

@@ -20,7 +20,10 @@ def files():
     paths = {}
     for name, data in (("a.txt", _corpus.make_text(3000, seed=11)), ("b.txt", _corpus.make_text(2000, seed=12, trailing_newline=False)),
                        ("para.txt", _corpus.make_text(2500, seed=13, paragraphs=True)),
-                       ("small.txt", _corpus.make_text(600, seed=14))):      # < 48 KiB: no block artefacts in -b
+                       ("small.txt", _corpus.make_text(600, seed=14)),       # < 48 KiB: no block artefacts in -b
+                       ("semi.txt", _corpus.make_text(300, seed=15).replace(b"\n", b";").replace(b"the", b"Hello", 30).replace(b"and", b"xhello", 10) + b"last hello"),
+                       ("blank.txt", b"\n" * 3000 + b"one the two\n" + b"\n" * 3000 + b"x\n\n\ny")):   # more than half of the bytes close a record
+
         paths[name] = os.path.join(d, name)
         open(paths[name], "wb").write(data)
     yield paths
@@ -60,6 +63,12 @@ CASES = [
     (["-n", "^the"], ["a.txt"]),
     (["-n", "world$"], ["b.txt"]),
     (["-n", "a#d;world"], ["a.txt"]),
+    (["-d", ";", "hello"], ["semi.txt"]),                        # sgrep keeps its engine under -d: ASCII case folded, bm() record cut
+    (["-c", "-d", ";", "hello"], ["semi.txt"]),
+    (["-c", "-w", "-d", ";", "hello"], ["semi.txt"]),
+    (["-n", "-v", "zzz"], ["blank.txt"]),                        # every blank line is a reported record (list longer than n/2)
+    (["-c", "-n", "^$"], ["blank.txt"]),
+    (["-n", "-1", "^$"], ["blank.txt"]),
 ]
 
 
@@ -74,7 +83,8 @@ def test_same_stdout_as_reference(files, args, names):
 
 
 CLI = os.path.join(ROOT, "agrep_b200", "agrep-b200")
-CLI_CASES = [c for c in CASES if not any(a in ("-L2", "-s") or a.startswith("-S") for a in c[0]) and c[0][-1] not in ("a#d;world",)]
+CLI_CASES = [c for c in CASES if not any(a in ("-L2", "-s") or a.startswith("-S") for a in c[0]) and c[0][-1] not in ("a#d;world",)
+             and "semi.txt" not in c[1]]
 
 
 @pytest.mark.parametrize("args,names", CLI_CASES)
@@ -87,3 +97,21 @@ def test_standalone_cli_prints_what_the_reference_prints(files, args, names):
     d = run(CLI, args + fl)
     assert d[1] == r[1]
     assert d[0] == r[0]
+
+
+MEM = os.path.join(ROOT, "oracle", "_ref", "memagrep_cli")
+MEMDROP = os.path.join(ROOT, "oracle", "_ref", "memagrep_dropin_cli")
+
+
+@pytest.mark.parametrize("args,name", [(["-n", "-1", "because each"], "a.txt"), (["-c", "-n", "-1", "the"], "a.txt"),
+                                       (["-c", "-n", "-1", "the"], "b.txt"), (["-n", "-2", "governmental"], "b.txt"),
+                                       (["-c", "-n", "the"], "b.txt"), (["-n", "-w", "-d", "$$", "world"], "para.txt")])
+def test_memory_mode_through_the_dropin(files, args, name):
+    """memagrep() (agrep.c:3282; scan loop bitap.c:309-446): the reference's in-memory entry point with the scan objects
+    replaced by the drop-in layer (fd == -1: the caller's buffer is scanned, no delimiter is appended behind it, so an
+    undelimited last record is not reported -- by -c either) prints and returns what the unmodified one does."""
+    if not (os.path.exists(MEM) and os.path.exists(MEMDROP)):
+        pytest.skip("oracle/_ref memagrep drivers not built")
+    r = run(MEM, [files[name], "-V0"] + args)
+    d = run(MEMDROP, [files[name], "-V0"] + args)
+    assert d[1] == r[1] and d[0] == r[0]

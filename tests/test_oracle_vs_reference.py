@@ -96,6 +96,48 @@ def test_sgrep_bm_counts(ref_agrep, pattern, kw, rargs, which):
     assert cnt == ref_count(ref_agrep, rargs + [pattern], data)
 
 
+@pytest.mark.parametrize("pattern,delim,kw,rargs", [
+    ("hello", ";", {}, []), ("HELLO", ";", {}, []), ("hello", ";", dict(wordbound=1), ["-w"]), ("each", "@#", {}, []),
+    ("state", ";", dict(nocase=1), ["-i"]), ("because each", "%", {}, []),
+    ("homogeneous approximate matching", ";", {}, []),          # > 20 characters: monkey() instead of bm() (sgrep.c:407-442, 1540)
+])
+def test_sgrep_keeps_its_engine_under_d(ref_agrep, pattern, delim, kw, rargs):
+    """checksg() does not look at -d: a simple literal at k=0 still goes to sgrep()/bm() -- ASCII case folded whatever -i
+    says -- and bm() cuts the records with backward_/forward_delimiter() (sgrep.c:775-795)."""
+    if not ref_agrep:
+        pytest.skip("reference binary not built")
+    body = TEXT[:30000].replace(b"\n", delim.encode(), 400).replace(b"the", b"Hello", 40).replace(b"and", b"xhello", 20)
+    for data in (b"Hello world;foo bar;HELLO again;nothing".replace(b";", delim.encode()), body, delim.encode() + body, body + delim.encode()):
+        a = _oracle.compile(pattern, delim=delim, **kw)
+        assert a.engine == 4
+        cnt, _ = _oracle.scan(a, data, want_records=False)
+        assert cnt == ref_count(ref_agrep, rargs + ["-d", delim, pattern], data), (pattern, delim, data[:40])
+
+
+@pytest.mark.parametrize("pattern", ["the of and to in that is was he for", "homogeneous approximate matching", "governmental homogeneous"])
+def test_sgrep_long_literals_take_monkey(ref_agrep, pattern):
+    """m > 20 (LONG_EXAC): the reference runs monkey() instead of bm() (sgrep.c:407-442, 1540-1834); same record semantics"""
+    if not ref_agrep:
+        pytest.skip("reference binary not built")
+    data = TEXT + (b"xx " + pattern.encode() + b" yy\n") * 3 + pattern.upper().encode() + b"\n" + TEXT[:5000]
+    a = _oracle.compile(pattern)
+    assert a.engine == 4 and a.litlen > 20
+    cnt, _ = _oracle.scan(a, data, want_records=False)
+    assert cnt >= 4 and cnt == ref_count(ref_agrep, [pattern], data)
+
+
+def test_latin1_fold_is_the_table_the_reference_ends_up_with(ref_agrep):
+    """-i at k=0 reads bytes through LUT[] (bitap.c:171) = CP[ISO-8859-1].lower_1 with the metasymbol bytes put back to
+    themselves (agrep.c:2835-2848): 0xC9 folds to 0xE9, but 0x83 does not fold to 'f', 0x8f not to 0x86, 0x99 not to 0x94"""
+    if not ref_agrep:
+        pytest.skip("reference binary not built")
+    data = b"\x83ood one\nfood two\nab\x99cd\nab\x94cd\ncaf\xc9 x\ncaf\xe9 y\nq\x8fq\nq\x86q\n"
+    for pat in (b"food", b"b\x94c", b"caf\xe9", b"q\x86q", b"\x83ood", b"b\x99c"):
+        a = _oracle.compile(pat, k=0, linenum=1, nocase=1)
+        cnt, recs = _oracle.scan(a, data)
+        assert [r[2] - 1 for r in recs] == ref_ordinals(ref_agrep, ["-i", pat], data), pat
+
+
 def test_random_differential(ref_agrep):
     """SURVEY appendix A differential driver: random substrings with 0-2 edits, k in 1..3, -n forced."""
     if not ref_agrep:
