@@ -53,7 +53,8 @@ class CorpusSpec(C.Structure):
 
 EXPORTS = ["agb_fill_ordinals", "agb_compile", "agb_pattern_free", "agb_pattern_desc", "agb_pattern_from_desc", "agb_scan_device",
            "agb_scan_host", "agb_scan_fd", "agb_bestmatch_device", "agb_corpus_fill_device", "agb_corpus_fill_host",
-           "agb_last_error", "agb_device_count", "agb_set_device", "agb_version", "agb_kernel_launches"]
+           "agb_last_error", "agb_device_count", "agb_set_device", "agb_version", "agb_kernel_launches",
+           "agb_text_from_host", "agb_text_from_fd", "agb_text_free", "agb_text_size", "agb_text_device", "agb_scan_text"]
 
 _lib = None
 
@@ -77,12 +78,21 @@ def lib():
     L.agb_scan_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(Result)]
     L.agb_scan_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(Result)]
     L.agb_scan_fd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(Result)]
-    L.agb_bestmatch_device.argtypes = [C.c_char_p, C.POINTER(Options), C.c_void_p, C.c_uint64, C.c_void_p,
+    L.agb_bestmatch_device.argtypes = [C.c_char_p, C.POINTER(Options), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
                                        C.POINTER(C.c_int), C.POINTER(Result), C.c_char_p, C.c_size_t]
     L.agb_corpus_fill_device.argtypes = [C.POINTER(CorpusSpec), C.c_void_p, C.c_void_p]
     L.agb_corpus_fill_host.argtypes = [C.POINTER(CorpusSpec), C.c_void_p]
     L.agb_fill_ordinals.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
     L.agb_fill_ordinals.restype = None
+    L.agb_text_from_host.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+    L.agb_text_from_fd.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.agb_text_free.argtypes = [C.c_void_p]
+    L.agb_text_free.restype = None
+    L.agb_text_size.argtypes = [C.c_void_p]
+    L.agb_text_size.restype = C.c_uint64
+    L.agb_text_device.argtypes = [C.c_void_p]
+    L.agb_text_device.restype = C.c_void_p
+    L.agb_scan_text.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(Result)]
     L.agb_last_error.restype = C.c_char_p
     L.agb_version.restype = C.c_char_p
     L.agb_kernel_launches.restype = C.c_uint64

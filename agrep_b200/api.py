@@ -78,8 +78,9 @@ class Pattern:
         return res
 
 
-def bestmatch_device(pattern, dev_ptr, n, stream=0, **kw):
-    """The -B sweep (agrep.c:3582-3728): returns (best_k or -1, Result)."""
+def bestmatch_device(pattern, dev_ptr, n, stream=0, d_records=0, capacity=0, **kw):
+    """The -B sweep (agrep.c:3582-3728): returns (best_k or -1, Result); with d_records/capacity (device buffer of Record)
+    also the ordered list of the records at the best level."""
     if isinstance(pattern, str):
         pattern = pattern.encode("latin-1")
     d = kw.pop("delim", None)
@@ -88,7 +89,7 @@ def bestmatch_device(pattern, dev_ptr, n, stream=0, **kw):
     o = Options(delim=d, **{k: int(v) for k, v in kw.items()})
     res, best, err = Result(), C.c_int(-1), C.create_string_buffer(512)
     rc = _lib.lib().agb_bestmatch_device(pattern, C.byref(o), C.c_void_p(dev_ptr), n, C.c_void_p(stream),
-                                        C.byref(best), C.byref(res), err, 512)
+                                        C.c_void_p(d_records), capacity, C.byref(best), C.byref(res), err, 512)
     if rc != 0:
         raise AgrepError(err.value.decode() or _lib.lib().agb_last_error().decode())
     return best.value, res

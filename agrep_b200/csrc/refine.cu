@@ -50,17 +50,23 @@ k_compact_ranges(const uint32_t *bitmap, uint64_t n_words, const uint64_t *range
 	const uint64_t n_groups = (n_words + 31) / 32, per = (n_groups + nwarps - 1) / nwarps;
 	const uint64_t g_begin = warp * per < n_groups ? warp * per : n_groups, g_end = (g_begin + per < n_groups) ? g_begin + per : n_groups;
 	uint64_t at = range_offsets[warp];
-	for (uint64_t g = g_begin; g < g_end; g++) {
-		const uint64_t w = g * 32 + lane;
-		const uint32_t word = w < n_words ? bitmap[w] : 0u;
-		if (!__ballot_sync(0xffffffffu, word != 0)) continue;
-		uint32_t c = __popc(word), pre = c;
+	for (uint64_t g0 = g_begin; g0 < g_end; g0 += 8) {      /* eight loads in flight: the survivors are few, the loop is all latency */
+		uint32_t wd[8];
 #pragma unroll
-		for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= (uint32_t)o) pre += v; }
-		const uint32_t total = __shfl_sync(0xffffffffu, pre, 31);
-		uint64_t mine = at + (pre - c);
-		for (uint32_t b = word; b; b &= b - 1) { if (mine < cap) list[mine] = w * 32 + (uint64_t)(__ffs(b) - 1); mine++; }
-		at += total;
+		for (int u = 0; u < 8; u++) { const uint64_t w = (g0 + u) * 32 + lane; wd[u] = (g0 + u < g_end && w < n_words) ? bitmap[w] : 0u; }
+#pragma unroll
+		for (int u = 0; u < 8; u++) {
+			const uint32_t word = wd[u];
+			if (!__ballot_sync(0xffffffffu, word != 0)) continue;
+			const uint64_t w = (g0 + u) * 32 + lane;
+			uint32_t c = __popc(word), pre = c;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= (uint32_t)o) pre += v; }
+			const uint32_t total = __shfl_sync(0xffffffffu, pre, 31);
+			uint64_t mine = at + (pre - c);
+			for (uint32_t b = word; b; b &= b - 1) { if (mine < cap) list[mine] = w * 32 + (uint64_t)(__ffs(b) - 1); mine++; }
+			at += total;
+		}
 	}
 }
 

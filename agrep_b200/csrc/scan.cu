@@ -434,33 +434,192 @@ extern "C" int agb_scan_fd(const agb_pattern *p, int fd, int want, agb_record *r
 	return rc;
 }
 
-/* agrep.c:3582-3728: when the exact pass finds nothing, -B looks for the smallest D in 1..min(M-1,8) with a
- * match, rescanning every file once per D.  The rows are nested (A_j contains A_{j-1}, asearch.c:98-114), so
- * ONE pass at the largest D yields every record's smallest level; level_hist tells the best D. */
+/* ---- a text kept in HBM across scans (the drop-in layer's exec() scans the same file K + 2 times under -B,
+ * agrep.c:3582-3728: one upload instead of K + 2) ---- */
+struct agb_text { uint8_t *d; uint64_t n; int dev; };
+
+static int text_upload(const SliceSource &src, uint64_t n, agb_text **out)
+{
+	int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
+	if (dev < 0 || dev >= 64) return AGB_ERR_ARG;
+	agb_text *t = new agb_text; t->d = nullptr; t->n = n; t->dev = dev;
+	const size_t need = (size_t)((n + 15) / 16 * 16 + 4096);
+	if (cudaMalloc(&t->d, need) != cudaSuccess) { delete t; snprintf(g_err, sizeof g_err, "cudaMalloc of %zu bytes for the text failed", need); cudaGetLastError(); return AGB_ERR_NOMEM; }
+	std::lock_guard<std::mutex> lk(g_ws_mu);
+	Workspace &W = g_ws[dev];
+	int rc = ws_prepare(W, 0); if (rc) { cudaFree(t->d); delete t; return rc; }
+	if (!W.s_copy) {
+		CUDA_TRY(cudaStreamCreateWithFlags(&W.s_copy, cudaStreamNonBlocking));
+		CUDA_TRY(cudaStreamCreateWithFlags(&W.s_comp, cudaStreamNonBlocking));
+		for (int i = 0; i < STAGE_BUFS; i++) CUDA_TRY(cudaEventCreateWithFlags(&W.ev_copy[i], cudaEventDisableTiming));
+	}
+	const bool direct = src.mem && src.pinned;
+	if (!direct && n && !W.stage[0]) for (int i = 0; i < STAGE_BUFS; i++) CUDA_TRY(cudaMallocHost(&W.stage[i], H2D_SLICE));
+	CUDA_TRY(cudaMemsetAsync(t->d + (n & ~(uint64_t)15), 0, need - (n & ~(uint64_t)15), W.s_copy));
+	const uint64_t n_slices = (n + H2D_SLICE - 1) / H2D_SLICE;
+	for (uint64_t i = 0; i < n_slices; i++) {
+		const uint64_t off = i * H2D_SLICE, len = std::min<uint64_t>(H2D_SLICE, n - off);
+		const int sb = (int)(i % STAGE_BUFS);
+		if (direct) CUDA_TRY(cudaMemcpyAsync(t->d + off, src.mem + off, len, cudaMemcpyHostToDevice, W.s_copy));
+		else {
+			if (i >= STAGE_BUFS) CUDA_TRY(cudaEventSynchronize(W.ev_copy[sb]));
+			if (src.mem) par_memcpy(W.stage[sb], src.mem + off, len);
+			else {
+				uint64_t got = 0;
+				while (got < len) {
+					ssize_t r = read(src.fd, W.stage[sb] + got, (size_t)(len - got));
+					if (r <= 0) { snprintf(g_err, sizeof g_err, "read(2) returned %zd at offset %llu of %llu", r, (unsigned long long)(off + got), (unsigned long long)n); cudaStreamSynchronize(W.s_copy); cudaFree(t->d); delete t; return AGB_ERR_ARG; }
+					got += (uint64_t)r;
+				}
+			}
+			CUDA_TRY(cudaMemcpyAsync(t->d + off, W.stage[sb], len, cudaMemcpyHostToDevice, W.s_copy));
+		}
+		CUDA_TRY(cudaEventRecord(W.ev_copy[sb], W.s_copy));
+	}
+	CUDA_TRY(cudaStreamSynchronize(W.s_copy));
+	*out = t;
+	return AGB_OK;
+}
+
+extern "C" int agb_text_from_host(const void *h_text, uint64_t n, agb_text **out)
+{
+	if (!out || (!h_text && n)) return AGB_ERR_ARG;
+	SliceSource src; src.mem = (const uint8_t *)h_text; src.fd = -1; src.pinned = false;
+	if (n) {
+		cudaPointerAttributes attr; memset(&attr, 0, sizeof attr);
+		src.pinned = cudaPointerGetAttributes(&attr, h_text) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+		cudaGetLastError();
+	}
+	return text_upload(src, n, out);
+}
+
+extern "C" int agb_text_from_fd(int fd, agb_text **out)
+{
+	if (!out) return AGB_ERR_ARG;
+	struct stat sb;
+	if (fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode)) { snprintf(g_err, sizeof g_err, "agb_text_from_fd needs a regular file"); return AGB_ERR_ARG; }
+	off_t cur = lseek(fd, 0, SEEK_CUR);
+	const uint64_t n = (cur >= 0 && sb.st_size > cur) ? (uint64_t)(sb.st_size - cur) : 0;
+	SliceSource src; src.mem = nullptr; src.pinned = false; src.fd = fd;
+	return text_upload(src, n, out);
+}
+
+extern "C" void agb_text_free(agb_text *t) { if (t) { cudaFree(t->d); delete t; } }
+extern "C" uint64_t agb_text_size(const agb_text *t) { return t ? t->n : 0; }
+extern "C" const void *agb_text_device(const agb_text *t) { return t ? t->d : nullptr; }
+
+/* device scan of a resident text with the record list delivered to host memory */
+static int scan_text_impl(const agb_desc &d, const agb_text *t, int want, int want_level, agb_record *records, uint64_t capacity, agb_result *res)
+{
+	if (!t || !res) return AGB_ERR_ARG;
+	if ((want & AGB_WANT_RECORDS) && capacity && !records) return AGB_ERR_ARG;
+	CUDA_TRY(cudaSetDevice(t->dev));
+	agb_record *d_rec = nullptr;
+	{
+		std::lock_guard<std::mutex> lk(g_ws_mu);
+		Workspace &W = g_ws[t->dev];
+		if ((want & AGB_WANT_RECORDS) && capacity > W.h2d_rec_cap) {
+			if (W.h2d_rec) cudaFree(W.h2d_rec);
+			W.h2d_rec = nullptr; W.h2d_rec_cap = 0;
+			CUDA_TRY(cudaMalloc(&W.h2d_rec, capacity * sizeof(agb_record))); W.h2d_rec_cap = capacity;
+		}
+		d_rec = W.h2d_rec;
+	}
+	int rc = scan_device_impl(d, t->d, t->n, want, want_level, d_rec, capacity, nullptr, res); if (rc) return rc;
+	if (res->n_records) CUDA_TRY(cudaMemcpy(records, d_rec, res->n_records * sizeof(agb_record), cudaMemcpyDeviceToHost));
+	return AGB_OK;
+}
+
+extern "C" int agb_scan_text(const agb_pattern *p, const agb_text *t, int want, agb_record *records, uint64_t capacity, agb_result *res)
+{
+	if (!p) return AGB_ERR_ARG;
+	return scan_text_impl(p->d, t, want, -1, records, capacity, res);
+}
+
+/* keep the records of one level (stable, in place: the output index never overtakes the input index) */
+__global__ void __launch_bounds__(1024) k_filter_level(agb_record *recs, uint64_t n, int level, unsigned long long *n_out)
+{
+	__shared__ unsigned long long s_warp[32];
+	__shared__ unsigned long long s_base;
+	const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	if (tid == 0) s_base = 0;
+	__syncthreads();
+	for (uint64_t t0 = 0; t0 < n; t0 += 1024) {
+		const uint64_t i = t0 + tid;
+		agb_record r; r.level = -1;
+		if (i < n) r = recs[i];
+		const bool keep = i < n && r.level == level;
+		const uint32_t m = __ballot_sync(0xffffffffu, keep);
+		if (lane == 0) s_warp[wid] = __popc(m);
+		__syncthreads();                                    /* every read of this tile is done */
+		unsigned long long before = s_base;
+		for (uint32_t w = 0; w < wid; w++) before += s_warp[w];
+		if (keep) recs[before + __popc(m & ((1u << lane) - 1u))] = r;
+		__syncthreads();
+		if (tid == 0) { unsigned long long t = 0; for (int w = 0; w < 32; w++) t += s_warp[w]; s_base += t; }
+		__syncthreads();
+	}
+	if (tid == 0) *n_out = s_base;
+}
+
+/* agrep.c:3582-3728: when the exact pass finds nothing, -B looks for the smallest D in 1..min(M-1,8) with a match,
+ * rescanning every file once per D, and then once more at that D to print.  The rows are nested (A_j contains A_{j-1},
+ * asearch.c:98-114), so ONE pass at a level k yields every record's smallest level <= k: the histogram tells the best
+ * level, the list -- filtered to that level on the device -- is what the printing pass would print.  The pass runs at
+ * k = 2 first (the anchor filter is still selective there; it also answers the exact question), then 4, then 8: one
+ * pass for every best level up to 2, at most three.
+ * best_k: smallest level with a match (-1: none up to min(M-1, 8)); res->n_matched: records at that level (what
+ * the reference reports as "N words match within K errors"); d_records/capacity: their ordered list (level filled). */
 extern "C" int agb_bestmatch_device(const char *pattern, const agb_options *opt, const void *d_text, uint64_t n,
-                                    void *stream, int *best_k, agb_result *res, char *err, size_t errlen)
+                                    void *stream, agb_record *d_records, uint64_t capacity, int *best_k, agb_result *res,
+                                    char *err, size_t errlen)
 {
 	if (!pattern || !opt || !best_k || !res) return AGB_ERR_ARG;
+	if (capacity && !d_records) return AGB_ERR_ARG;
 	agb_options o = *opt; agb_desc d; int m = (int)strlen(pattern);
+	cudaStream_t st = (cudaStream_t)stream;
 	o.bestmatch = 1;
 	*best_k = -1;
 	/* D < M of the exact pattern (agrep.c:3594); M there counts the delimiter and separator too */
 	o.k = 0;
 	int rc = agbi_build(pattern, &o, &d, err, errlen); if (rc) return rc;
 	int kmax = d.M - 1; if (kmax > AGB_MAXERR) kmax = AGB_MAXERR; if (kmax > m - 1) kmax = m - 1;
-	/* staged doubling keeps the anchor filter selective: k = 0, then 2, 4, 8 */
-	int stages[5] = { 0, 2, 4, 8, 8 }, prev = -1;
-	for (int si = 0; si < 4; si++) {
+	const int want = AGB_WANT_LEVELS | (capacity ? AGB_WANT_RECORDS : AGB_WANT_COUNT);
+	int stages[3] = { 2, 4, 8 }, prev = -1;
+	for (int si = 0; si < 3; si++) {
 		int k = stages[si] < kmax ? stages[si] : kmax;
 		if (k <= prev) break;
 		o.k = k;
 		rc = agbi_build(pattern, &o, &d, err, errlen); if (rc) return rc;
-		rc = scan_device_impl(d, d_text, n, AGB_WANT_COUNT | AGB_WANT_LEVELS, -1, nullptr, 0, (cudaStream_t)stream, res);
+		rc = scan_device_impl(d, d_text, n, want, -1, d_records, capacity, st, res);
 		if (rc) return rc;
-		for (int l = prev + 1; l <= k; l++) if (res->level_hist[l]) { *best_k = l; res->n_matched = res->level_hist[l]; return AGB_OK; }
-		/* levels <= prev were already known to be empty */
+		int best = -1;
+		for (int l = prev + 1; l <= k; l++) if (res->level_hist[l]) { best = l; break; }    /* levels <= prev were already known to be empty */
 		prev = k;
+		if (best < 0) continue;
+		*best_k = best;
+		const uint64_t n_best = res->level_hist[best];
+		if (capacity) {
+			if (res->truncated) {
+				/* the list of all levels up to k did not fit: once more, at the best level only */
+				o.k = best;
+				rc = agbi_build(pattern, &o, &d, err, errlen); if (rc) return rc;
+				agb_result r2;
+				rc = scan_device_impl(d, d_text, n, want, best, d_records, capacity, st, &r2); if (rc) return rc;
+				res->n_records = r2.n_records; res->truncated = r2.truncated;
+			} else if (best < k && res->n_records) {
+				int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
+				std::lock_guard<std::mutex> lk(g_ws_mu);
+				Workspace &W = g_ws[dev];
+				k_filter_level<<<1, 1024, 0, st>>>(d_records, res->n_records, best, W.totals + 15); g_launches++;
+				CUDA_TRY(cudaGetLastError());
+				CUDA_TRY(cudaStreamSynchronize(st));
+				res->n_records = std::min<uint64_t>(n_best, capacity);
+			}
+		}
+		res->n_matched = n_best;
+		return AGB_OK;
 	}
-	res->n_matched = 0;
+	res->n_matched = 0; res->n_records = 0;
 	return AGB_OK;
 }

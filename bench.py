@@ -39,6 +39,58 @@ def peaks():
         return 6650.0, "fallback 6.65 TB/s (of fallback)"
 
 
+def host_cores():
+    """the cores this process may actually use: scheduler affinity, cut by the cgroup CPU quota when there is one"""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    quota = None
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            f = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if f[0] != "max":
+                    quota = float(f[0]) / float(f[1])
+            else:
+                q = float(f[0])
+                if q > 0:
+                    quota = q / float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            break
+        except Exception:
+            continue
+    usable = n if quota is None else max(1, min(n, int(quota + 0.5)))
+    return {"os_cpu_count": os.cpu_count(), "affinity": n, "cgroup_quota_cpus": quota, "usable": usable}
+
+
+def all_core_reference(ag, cores, shard_mib, steps=2):
+    """`cores` unmodified reference processes at once, each over its own shard of the synthetic corpus (the program is
+    single-threaded by construction): GB/s of the whole box, (matches, bytes) of one pass"""
+    shard = (shard_mib << 20) // PAGE * PAGE
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > cores * shard * 1.2 else tempfile.gettempdir()
+    tmp = tempfile.mkdtemp(prefix="agb_ref_", dir=base)
+    try:
+        files = [os.path.join(tmp, "shard%03d.txt" % i) for i in range(cores)]
+
+        def gen(i):
+            data = ag.corpus_host(shard, first_page=i * (shard // PAGE), needle=PATTERN, needle_every=NEEDLE_EVERY, needle_maxedits=3)
+            with open(files[i], "wb") as f:
+                f.write(data)
+        th = [threading.Thread(target=gen, args=(i,)) for i in range(cores)]
+        [t.start() for t in th]; [t.join() for t in th]
+        best, matched = None, 0
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            ps = [subprocess.Popen([REF_BIN, "-V0", "-c", "-n", "-%d" % K, PATTERN, f], stdout=subprocess.PIPE,
+                                   stderr=subprocess.DEVNULL) for f in files]
+            matched = sum(int((p.communicate()[0] or b"0").split()[0]) if p.wait() is not None else 0 for p in ps)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        return shard * cores / best / 1e9, matched, shard * cores
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -95,7 +147,8 @@ def run_reference(args):
     if rank != 0:
         return 0
     import agrep_b200 as ag
-    cores = os.cpu_count() or 1
+    hc = host_cores()
+    cores = hc["usable"]
     kind = "reference" if os.path.exists(REF_BIN) else "port"
     shard = (256 << 20) // PAGE * PAGE      # large enough that process start-up is noise next to the scan
     base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > cores * shard * 1.2 else tempfile.gettempdir()
@@ -133,12 +186,13 @@ def run_reference(args):
             matched = step()
         dt = (time.perf_counter() - t0) / max(1, args.steps)
         val = total / dt / 1e9
-        sample = "%d shards x %d MiB of the same synthetic corpus, one `agrep -V0 -c -n -%d` process per host core" % (cores, shard >> 20, K)
+        sample = ("%d shards x %d MiB = %.1f GiB of the same synthetic corpus per step (a bounded sample of the %.0f GiB workload; GB/s is "
+                  "size-normalised), one `agrep -V0 -c -n -%d` process per usable host core" % (cores, shard >> 20, total / (1 << 30), TOTAL_GIB, K))
         print(json.dumps({
             "impl": "reference", "metric": "text_scan_throughput", "value": val, "unit": "GB/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u32 bitwise", "data": "synthetic",
-            "config": workload_config(args.gpus), "matches_per_step": matched,
+            "config": workload_config(args.gpus), "matches_per_step": matched, "scanned_bytes_per_step": total, "host_cores": hc,
             "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
     finally:
@@ -186,9 +240,21 @@ def cpu_baseline(ag, corpus_t, n_local):
             t0 = time.perf_counter()
             count = _oracle.scan(a, data, want_records=False)[0]
             best = time.perf_counter() - t0
-        return {"value": nbytes / best / 1e9, "unit": "GB/s", "cores": 1, "kind": kind,
-                "sample": "first %d MiB of the benchmark corpus, `agrep -V0 -c -n -%d '%s'`, page-cached, best of 2" % (nbytes >> 20, K, PATTERN),
-                "matched_in_sample": count, "host_cores_available": os.cpu_count()}, nbytes, count
+        ordinals = None
+        if kind == "reference":
+            # the matching lines themselves, not just how many: -n prints j - 1 in front of every record (agrep.c:3878)
+            import re
+            out = subprocess.run([REF_BIN, "-V0", "-n", "-%d" % K, PATTERN, path], capture_output=True).stdout
+            ordinals = [int(m.group(1)) for m in re.finditer(rb"^(\d+): ", out, re.M)]
+        hc = host_cores()
+        res = {"value": nbytes / best / 1e9, "unit": "GB/s", "cores": 1, "kind": kind,
+               "sample": "first %d MiB of the benchmark corpus, `agrep -V0 -c -n -%d '%s'`, page-cached, best of 2" % (nbytes >> 20, K, PATTERN),
+               "matched_in_sample": count, "host_cores": hc}
+        if kind == "reference" and hc["usable"] > 1:
+            v, m, b = all_core_reference(ag, hc["usable"], 128)
+            res["all_cores"] = {"value": v, "unit": "GB/s", "cores": hc["usable"], "kind": kind,
+                                "sample": "%d reference processes at once, %d MiB of the same corpus each, best of 2" % (hc["usable"], 128)}
+        return res, nbytes, count, ordinals
     finally:
         try:
             os.unlink(path)
@@ -196,11 +262,16 @@ def cpu_baseline(ag, corpus_t, n_local):
             pass
 
 
-def secondary_workloads(ag, torch, corpus, n_local, stream):
-    """The other BASELINE.json configs, measured on the side (not the headline): count-only device scans, best of 3,
-    CUDA-event stage times from the library.  configs[0]-like: 'the' (sgrep/bm path, one line in three matches);
-    configs[2]: 32-char pattern, -3 -w, paragraph records on a 16 GiB paragraph corpus; configs[3]: -i -B sweep."""
+def secondary_workloads(ag, torch, corpus, n_local, stream, peak):
+    """The other BASELINE.json configs at the full corpus size, measured on the side (not the headline): device scans,
+    best of 3, CUDA-event stage times from the library, each with its own roofline fraction (corpus bytes / time against
+    the measured HBM figure).  configs[0] at scale: 'the' (sgrep/bm semantics, one line in three matches); configs[3]:
+    -i -B best match; the headline query with -n; configs[2] last, because its paragraph corpus overwrites the text:
+    32-char pattern, -3 -w, paragraph records."""
     out = []
+
+    def roof(n, ms):
+        return {"bound": "hbm", "achieved": n / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": n / ms / 1e6 / peak}
 
     def timed(pat, data_ptr, n, **kw):
         p = ag.Pattern(pat, **kw)
@@ -215,21 +286,11 @@ def secondary_workloads(ag, torch, corpus, n_local, stream):
         d = p.desc
         return {"pattern": pat, "options": {k: (v if isinstance(v, (int, str)) else int(v)) for k, v in kw.items()},
                 "bytes": n, "ms": t, "gb_s": n / t / 1e6, "ms_stage1": r.ms_front, "matched": int(r.n_matched),
-                "plan": "anchors" if d.plan == 1 else "all", "n_anchors": int(d.n_anchors)}
+                "plan": "anchors" if d.plan == 1 else "all", "n_anchors": int(d.n_anchors), "roofline": roof(n, t)}
     try:
         o = timed("the", corpus.data_ptr(), n_local)
         o["config"] = "configs[0] at scale: agrep -c the (sgrep/bm semantics)"
         out.append(o)
-        n2 = min(16 << 30, n_local) // PAGE * PAGE
-        para = torch.empty(n2 + 4096, dtype=torch.uint8, device=corpus.device)
-        para[n2:].zero_()
-        p32 = "business give group toward young"
-        ag.corpus_device(para.data_ptr(), n2, stream=stream, paragraphs=True, needle=p32, needle_every=NEEDLE_EVERY, needle_maxedits=4)
-        torch.cuda.synchronize()
-        o = timed(p32, para.data_ptr(), n2, k=3, wordbound=True, linenum=True, delim="$$")
-        o["config"] = "configs[2]: 32-char pattern, -3 -w -d '$$' (M = 37: 64-bit rows; the reference refuses it)"
-        out.append(o)
-        del para
         # the headline query with -n: the ordered list plus every record's ordinal (j), counted on the device
         cap = 1 << 22
         rec = torch.empty((cap, 4), dtype=torch.int64, device=corpus.device)
@@ -246,15 +307,31 @@ def secondary_workloads(ag, torch, corpus, n_local, stream):
         ords = rec[:nr, 2]
         out.append({"config": "the headline query with -n (AGB_WANT_RECORDS | AGB_WANT_ORDINALS): list + ordinals (stage 1 also counts the delimiters of every 512-byte block)",
                     "pattern": PATTERN, "bytes": n_local, "ms": t, "gb_s": n_local / t / 1e6, "matched": int(r.n_matched),
-                    "n_closes": int(r.n_closes), "ordinals_increasing": bool(nr < 2 or bool((ords[1:] > ords[:-1]).all().item()))})
-        del rec
-        t0 = time.perf_counter()
-        best, res = ag.bestmatch_device("Becuase Each Just Th", corpus.data_ptr(), n_local, stream=stream, nocase=1)
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) * 1e3
-        out.append({"config": "configs[3]: -i -B best-match sweep (agrep.c:3582-3728), 20-char mixed-case pattern",
+                    "n_closes": int(r.n_closes), "ordinals_increasing": bool(nr < 2 or bool((ords[1:] > ords[:-1]).all().item())),
+                    "roofline": roof(n_local, t)})
+        # configs[3]: the -B sweep as ONE pass at the largest level: best level, its count and its ordered record list
+        bestb = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            best, res = ag.bestmatch_device("Becuase Each Just Th", corpus.data_ptr(), n_local, stream=stream, nocase=1,
+                                            d_records=rec.data_ptr(), capacity=cap)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) * 1e3
+            if bestb is None or dt < bestb[0]:
+                bestb = (dt, best, res)
+        dt, best, res = bestb
+        out.append({"config": "configs[3]: -i -B best match (agrep.c:3582-3728), 20-char mixed-case pattern: best level + its records",
                     "pattern": "Becuase Each Just Th", "bytes": n_local, "ms": dt, "gb_s": n_local / dt / 1e6,
-                    "best_k": int(best), "matched": int(res.n_matched)})
+                    "best_k": int(best), "matched": int(res.n_matched), "records_returned": int(res.n_records),
+                    "timing": "wall clock around the call (it may run more than one device pass)", "roofline": roof(n_local, dt)})
+        del rec
+        # configs[2] on the whole corpus size: the paragraph variant overwrites the text (nothing needs it after this)
+        p32 = "business give group toward young"
+        ag.corpus_device(corpus.data_ptr(), n_local, stream=stream, paragraphs=True, needle=p32, needle_every=NEEDLE_EVERY, needle_maxedits=4)
+        torch.cuda.synchronize()
+        o = timed(p32, corpus.data_ptr(), n_local, k=3, wordbound=True, linenum=True, delim="$$")
+        o["config"] = "configs[2]: 32-char pattern, -3 -w -d '$$', paragraph records (M = 37: 64-bit rows; the reference refuses it)"
+        out.append(o)
     except Exception as e:      # a secondary measurement must never take the headline down
         out.append({"error": repr(e)})
     return out
@@ -343,13 +420,16 @@ def main():
     host = torch.empty(n_e2e, dtype=torch.uint8, pin_memory=True)
     host.copy_(corpus[:n_e2e])
     torch.cuda.synchronize()
-    hrec = (_lib.Record * 65536)()
+    E2E_CAP = max(1 << 20, n_e2e // 4096)       # (the 4 GiB slice holds about 96 k matching records)
+    hrec = (_lib.Record * E2E_CAP)()
     hres = _lib.Result()
 
     def e2e_step():
-        rc = L.agb_scan_host(pat._h, ctypes.c_void_p(host.data_ptr()), n_e2e, _lib.WANT_RECORDS, hrec, 65536, ctypes.byref(hres))
+        rc = L.agb_scan_host(pat._h, ctypes.c_void_p(host.data_ptr()), n_e2e, _lib.WANT_RECORDS, hrec, E2E_CAP, ctypes.byref(hres))
         if rc != 0:
             raise RuntimeError(L.agb_last_error().decode())
+        if hres.truncated:
+            raise RuntimeError("e2e: the record list did not fit (%d matches)" % hres.n_matched)
         return hres.n_records
     for _ in range(2):
         e2e_step()
@@ -367,16 +447,23 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1:
-        cpu, nsample, cpu_count = cpu_baseline(ag, corpus, n_local)
-        # the same sample through the CUDA path must agree with the reference binary, bit for bit
-        r = pat.scan_device(corpus.data_ptr(), nsample, stream=stream)
+        cpu, nsample, cpu_count, cpu_ordinals = cpu_baseline(ag, corpus, n_local)
+        # the same sample through the CUDA path must agree with the reference binary, bit for bit: the count and which
+        # lines they are (the ordinals the device computes against the reference's -n prefixes)
+        pn = ag.Pattern(PATTERN, k=K, linenum=True)
+        r = pn.scan_device(corpus.data_ptr(), nsample, stream=stream, d_records=recs.data_ptr(), capacity=CAP, ordinals=True)
         cpu["gpu_matched_in_sample"] = int(r.n_matched)
         if cpu_count is not None and int(r.n_matched) != cpu_count:
             raise SystemExit("PARITY FAILURE: reference counted %d records in the sample, CUDA path %d" % (cpu_count, r.n_matched))
+        if cpu_ordinals is not None:
+            got = (recs[:int(r.n_records), 2] - 1).cpu().tolist()
+            if got != cpu_ordinals:
+                raise SystemExit("PARITY FAILURE: the matching lines of the sample differ from the reference's (-n ordinals)")
+            cpu["ordinals_checked"] = len(got)
 
     secondary = None
     if rank == 0 and world == 1 and os.environ.get("AGB_BENCH_SECONDARY", "1") != "0":
-        secondary = secondary_workloads(ag, torch, corpus, n_local, stream)
+        secondary = secondary_workloads(ag, torch, corpus, n_local, stream, peaks()[0])
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -388,6 +475,16 @@ def main():
         except Exception:
             pass
         value = total / (ms_step * 1e-3) / 1e9
+        step_traffic = None
+        try:
+            step_traffic = json.load(open(os.path.join(ROOT, "profiles", "step_traffic.json")))
+        except Exception:
+            pass
+        roofline_step = {"bound": "hbm", "what": "the whole step (stage 1 + stage 1.5 + record stage + ordered list), per GPU",
+                         "achieved": n_local / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": n_local / (ms_step * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_step": n_local,
+                         "traffic": (step_traffic or {}).get("dram_bytes_per_step"),
+                         "traffic_note": (step_traffic or {}).get("note", "no ncu capture of a whole step yet")}
         out = {
             "metric": "text_scan_throughput", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
@@ -399,6 +496,7 @@ def main():
                          "stage2_ms_per_step": statistics.mean(rec_ms),
                          "traffic": (traffic or {}).get("dram_bytes_per_launch") if traffic else None,
                          "traffic_note": (traffic or {}).get("note") if traffic else "no ncu --set full capture yet"},
+            "roofline_step": roofline_step,
             "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": n_e2e, "d2h_bytes_per_step": 128 + 32 * int(nrec),
                     "what": "agb_scan_host() on a pinned host buffer holding the first %.1f GiB of each rank's shard; "
                             "64 MiB H2D slices overlapped with stage 1; wall clock incl. result read-back" % (n_e2e / (1 << 30))},

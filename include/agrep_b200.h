@@ -147,14 +147,30 @@ int  agb_scan_host(const agb_pattern *p, const void *h_text, uint64_t n, int wan
 /* file descriptor: read(2) loop into the pinned ring, as agb_scan_host */
 int  agb_scan_fd(const agb_pattern *p, int fd, int want, agb_record *records, uint64_t capacity, agb_result *res);
 
+/* ---- a text kept in HBM across scans ----
+ * exec() scans the same file up to K + 2 times under -B (agrep.c:3582-3728); the drop-in layer uploads it once.
+ * agb_text_from_fd: regular files, from the current offset to EOF, read(2) straight into the pinned ring. */
+typedef struct agb_text agb_text;
+int  agb_text_from_host(const void *h_text, uint64_t n, agb_text **out);
+int  agb_text_from_fd(int fd, agb_text **out);
+void agb_text_free(agb_text *t);
+uint64_t agb_text_size(const agb_text *t);
+const void *agb_text_device(const agb_text *t);
+/* as agb_scan_device over the resident text, the record list delivered to HOST memory */
+int  agb_scan_text(const agb_pattern *p, const agb_text *t, int want, agb_record *records, uint64_t capacity, agb_result *res);
+
 /* j of every record in `records` (ordered, as returned by a scan of h_text[0..n)): the number of record closes
  * up to and including its own (bitap.c:178), with the file-starts-with-the-delimiter correction of bitap.c:151-156.
  * A host walk over the delimiters, only needed for -n. */
 void agb_fill_ordinals(const agb_pattern *p, const void *h_text, uint64_t n, agb_record *records, uint64_t n_records);
 
-/* the -B sweep of agrep.c:3582-3728 as ONE extra pass: smallest k in 1..min(M-1,8) with a match */
+/* the -B sweep of agrep.c:3582-3728 in one pass for every best level up to 2 (at most three: k = 2, 4, 8): best_k =
+ * smallest level 0..min(M-1,8) at which a record matches (-1: none), res->n_matched = the records at that level (the
+ * reference's "N words match within K errors"), d_records[0..res->n_records) = their ordered list (what the final
+ * printing pass, agrep.c:3673-3726, prints); capacity 0: count only */
 int  agb_bestmatch_device(const char *pattern, const agb_options *opt, const void *d_text, uint64_t n,
-                          void *stream, int *best_k, agb_result *res, char *err, size_t errlen);
+                          void *stream, agb_record *d_records, uint64_t capacity, int *best_k, agb_result *res,
+                          char *err, size_t errlen);
 
 /* ---- synthetic corpus (bench / tests): deterministic, identical on host and device ---- */
 typedef struct agb_corpus_spec {

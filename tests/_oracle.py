@@ -65,7 +65,7 @@ def scan(a, text, want_records=True, cap=None):
     n = len(text)
     if not want_records:
         return lib().orc_scan(C.byref(a), text, n, None, 0), []
-    cap = cap or (n // 2 + 16)
+    cap = cap or (n + 2)          # an empty record is a record: up to one per text byte
     recs = (Record * cap)()
     cnt = lib().orc_scan(C.byref(a), text, n, recs, cap)
     return cnt, [(recs[i].begin, recs[i].end, recs[i].ordinal) for i in range(min(cnt, cap))]
@@ -73,7 +73,7 @@ def scan(a, text, want_records=True, cap=None):
 
 def scan_levels(a, kmax, text, want_level=-1, cap=None):
     n = len(text)
-    cap = cap or (n // 2 + 16)
+    cap = cap or (n + 2)          # an empty record is a record: up to one per text byte
     recs = (Record * cap)()
     hist = (C.c_uint64 * 9)()
     cnt = lib().orc_scan_levels(C.byref(a), kmax, text, n, hist, recs, cap, want_level)

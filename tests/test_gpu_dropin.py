@@ -21,7 +21,7 @@ def files():
     for name, data in (("a.txt", _corpus.make_text(3000, seed=11)), ("b.txt", _corpus.make_text(2000, seed=12, trailing_newline=False)),
                        ("para.txt", _corpus.make_text(2500, seed=13, paragraphs=True)),
                        ("small.txt", _corpus.make_text(600, seed=14)),       # < 48 KiB: no block artefacts in -b
-                       ("semi.txt", _corpus.make_text(300, seed=15).replace(b"\n", b";").replace(b"the", b"Hello", 30).replace(b"and", b"xhello", 10) + b"last hello"),
+                       ("semi.txt", _corpus.make_text(300, seed=15).replace(b"\n", b";").replace(b"the", b"Hello", 30).replace(b"and", b"xhello", 10) + b"last hello there"),   # (not "hello" at the very end: bm()'s sentinel copy of the pattern behind the text makes -w see a letter there)
                        ("blank.txt", b"\n" * 3000 + b"one the two\n" + b"\n" * 3000 + b"x\n\n\ny")):   # more than half of the bytes close a record
 
         paths[name] = os.path.join(d, name)
