@@ -54,7 +54,16 @@ class CorpusSpec(C.Structure):
 EXPORTS = ["agb_fill_ordinals", "agb_compile", "agb_pattern_free", "agb_pattern_desc", "agb_pattern_from_desc", "agb_scan_device",
            "agb_scan_host", "agb_scan_fd", "agb_bestmatch_device", "agb_corpus_fill_device", "agb_corpus_fill_host",
            "agb_last_error", "agb_device_count", "agb_set_device", "agb_version", "agb_kernel_launches",
-           "agb_text_from_host", "agb_text_from_fd", "agb_text_free", "agb_text_size", "agb_text_device", "agb_scan_text"]
+           "agb_text_from_host", "agb_text_from_fd", "agb_text_free", "agb_text_size", "agb_text_device", "agb_scan_text",
+           "agb_comm_unique_id", "agb_comm_init", "agb_comm_free", "agb_comm_world", "agb_comm_rank", "agb_shard_halo",
+           "agb_scan_sharded", "agb_scan_shard_local", "agb_bestmatch_sharded"]
+
+HALO_LEFT, HALO_RIGHT = 512, 65536
+
+
+class ShardPart(C.Structure):
+    _fields_ = [("closes", C.c_uint64), ("ord_fix", C.c_int64), ("ord_origin", C.c_int64), ("byte_base", C.c_int64),
+                ("virt", C.c_int32), ("pad", C.c_int32)]
 
 _lib = None
 
@@ -93,6 +102,19 @@ def lib():
     L.agb_text_device.argtypes = [C.c_void_p]
     L.agb_text_device.restype = C.c_void_p
     L.agb_scan_text.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(Result)]
+    L.agb_comm_unique_id.argtypes = [C.c_void_p]
+    L.agb_comm_init.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]
+    L.agb_comm_free.argtypes = [C.c_void_p]
+    L.agb_comm_free.restype = None
+    L.agb_comm_world.argtypes = [C.c_void_p]
+    L.agb_comm_rank.argtypes = [C.c_void_p]
+    L.agb_shard_halo.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.agb_scan_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64,
+                                   C.c_void_p, C.POINTER(Result)]
+    L.agb_scan_shard_local.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(Result), C.POINTER(ShardPart)]
+    L.agb_bestmatch_sharded.argtypes = [C.c_char_p, C.POINTER(Options), C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p,
+                                        C.c_uint64, C.c_void_p, C.POINTER(C.c_int), C.POINTER(Result), C.c_char_p, C.c_size_t]
     L.agb_last_error.restype = C.c_char_p
     L.agb_version.restype = C.c_char_p
     L.agb_kernel_launches.restype = C.c_uint64

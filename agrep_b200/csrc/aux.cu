@@ -367,6 +367,7 @@ int ordinals_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_
 	W.ord_virt = (d.L == 1 && d.delim[0] == '\n') ? 1 : 0;
 	/* bitap.c:151-156: j starts at -1 when the text begins with the user's delimiter (asearch0() has no such correction) */
 	P.j0 = (d.user_delim && d.engine != AGB_ENGINE_ASEARCH0 && n >= (uint64_t)d.L && memcmp(h_head, d.delim, (size_t)d.L) == 0) ? -1 : 0;
+	W.ord_j0 = P.j0;
 	if (blocks_counted) { k_ord_tiles<<<(unsigned)((tiles + 255) / 256), 256, 0, st>>>(P, tiles); g_launches++; }     /* stage 1 counted the blocks */
 	else { k_delim_count<<<(unsigned)tiles, ORD_THREADS, 0, st>>>(P); g_launches++; }
 	k_scan_tiles<<<1, 1024, 0, st>>>(W.tile_counts, W.tile_offsets, tiles, W.totals + 13); g_launches++;

@@ -62,7 +62,7 @@ __device__ __forceinline__ uint32_t chunk_records(const RecParams &P, const DevC
 		}
 		if (close_at < 0) { done_until = limit + 1; break; }           /* never closed: dropped, as the reference does */
 		const int64_t end = close_at + 1 - L;
-		const bool counts = (begin + 1 < n) && (begin + 1 <= end);       /* bitap.c:213 + agrep.c:3811 */
+		const bool counts = (begin + 1 < n) && (begin + 1 <= end) && rec_owned(P, begin, L, close_at);       /* bitap.c:213 + agrep.c:3811 */
 		int level = C.k;
 		bool cond;
 		if (P.levels) {
@@ -227,6 +227,7 @@ k_records_dense(const RecParams P)
 	for (int r = 0; r < NR; r++) RS[r] = SH.reset[r];
 	/* away from the end of the text every record counts unless it is empty (bitap.c:213, agrep.c:3811) */
 	const bool easy = tile0 + (int64_t)DENSE_TILE + DENSE_TAIL + L + 2 < n;
+	const bool sharded = P.own_lo > INT64_MIN / 2 || P.own_hi < INT64_MAX / 2;
 	uint32_t my_count = 0;
 	uint64_t out_pos = 0;
 	for (int pass = 0; pass < (P.emit ? 2 : 1); pass++) {
@@ -256,6 +257,7 @@ k_records_dense(const RecParams P)
 						const uint32_t end_rel = rel + 1 - L;
 						bool counts = (int32_t)(end_rel - begin_rel) >= 1;
 						if (!easy) counts = counts && (tile0 + (int64_t)(int32_t)begin_rel + 1 < n);
+						if (sharded) counts = counts && rec_owned(P, tile0 + (int64_t)(int32_t)begin_rel, L, tile0 + rel);
 						cnt += (match_cond<T>(S[NR - 1], C) && counts) ? 1u : 0u;
 						if (--left == 0) break;
 #pragma unroll
@@ -270,6 +272,7 @@ k_records_dense(const RecParams P)
 					const uint32_t end_rel = rel + 1 - L;
 					bool counts = (int32_t)(end_rel - begin_rel) >= 1;  /* begin + 1 <= end (agrep.c:3811) */
 					if (!easy) counts = counts && (tile0 + (int64_t)(int32_t)begin_rel + 1 < n);
+					if (sharded) counts = counts && rec_owned(P, tile0 + (int64_t)(int32_t)begin_rel, L, tile0 + rel);
 					int level = C.k;
 					bool cond;
 					if (P.levels) {
@@ -304,7 +307,7 @@ k_records_dense(const RecParams P)
 					rows_step<T, NR, COSTS>(S, SH.mask[R.get(p)], C);
 					if (S[0] & C.dendpos) {
 						const int64_t end = p + 1 - L;
-						const bool counts = (begin + 1 < n) && (begin + 1 <= end);
+						const bool counts = (begin + 1 < n) && (begin + 1 <= end) && rec_owned(P, begin, L, p);
 						int level = C.k;
 						bool cond;
 						if (P.levels) {

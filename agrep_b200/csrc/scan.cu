@@ -38,8 +38,8 @@ extern "C" int agb_set_device(int dev) { CUDA_TRY(cudaSetDevice(dev)); return AG
  * host side of the scan
  * ============================================================================================== */
 
-static Workspace g_ws[64];
-static std::mutex g_ws_mu;
+Workspace g_ws[64];
+std::mutex g_ws_mu;
 
 static int ws_prepare(Workspace &W, uint64_t n)
 {
@@ -138,7 +138,7 @@ static int list_stage(const agb_desc &d, Workspace &W, RecParams &P, bool want_l
  * here needs the host to know how many there are (the list is sized by W.cand_hint / a fraction of the chunks; the
  * caller checks totals[12] against W.cand_cap afterwards and comes back with refined_retry set if it was too small). */
 static int records_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, bool use_front, bool refined, int want,
-                          int want_level, agb_record *d_records, uint64_t capacity, cudaStream_t st)
+                          int want_level, agb_record *d_records, uint64_t capacity, cudaStream_t st, const ShardInfo *sh)
 {
 	const uint64_t n_chunks = (n + 15) / 16, n_words = (n_chunks + 31) / 32, tiles = (n_words + REC_THREADS - 1) / REC_THREADS;
 	RecParams P; memset(&P, 0, sizeof P);
@@ -146,6 +146,7 @@ static int records_launch(const agb_desc &d, Workspace &W, const void *d_text, u
 	P.n = n; P.n_chunks = n_chunks; P.n_words = n_words; P.desc = W.d_desc;
 	P.records = d_records; P.capacity = capacity;
 	P.totals = W.totals; P.emit = 0; P.levels = (want & AGB_WANT_LEVELS) ? 1 : 0; P.want_level = want_level;
+	P.own_lo = sh ? sh->own_lo : INT64_MIN; P.own_hi = sh ? sh->own_hi : INT64_MAX; P.shard_last = sh ? sh->last : 1;
 	if (!tiles) return AGB_OK;
 	const bool want_list = (want & AGB_WANT_RECORDS) && capacity;
 	if (use_front && refined) {
@@ -236,7 +237,8 @@ static int ordinals_prepare_blocks(const agb_desc &d, Workspace &W, uint64_t n, 
  * survivors there are; should it turn out too small (totals[12] > capacity, seen in the read-back) the record stage
  * alone is run again with the right size -- or in its every-byte form when the survivors are dense. */
 static int stages_after_front(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, bool use_front, bool count_in_front,
-                              int want, int want_level, agb_record *d_records, uint64_t capacity, cudaStream_t st, agb_result *res)
+                              int want, int want_level, agb_record *d_records, uint64_t capacity, cudaStream_t st, agb_result *res,
+                              const ShardInfo *sh = nullptr)
 {
 	int rc;
 	const uint64_t n_chunks = (n + 15) / 16;
@@ -244,7 +246,7 @@ static int stages_after_front(const agb_desc &d, Workspace &W, const void *d_tex
 	bool refined = false;
 	if (use_front) { rc = refine_launch(d, W, d_text, n, st, &refined); if (rc) return rc; }
 	for (int attempt = 0; ; attempt++) {
-		rc = records_launch(d, W, d_text, n, use_front, refined, want, want_level, d_records, capacity, st); if (rc) return rc;
+		rc = records_launch(d, W, d_text, n, use_front, refined, want, want_level, d_records, capacity, st, sh); if (rc) return rc;
 		if (want & AGB_WANT_ORDINALS) { rc = ordinals_launch(d, W, d_text, n, (want & AGB_WANT_RECORDS) ? d_records : nullptr, capacity, st, count_in_front); if (rc) return rc; }
 		CUDA_TRY(cudaEventRecord(W.e2, st));
 		rc = fetch_result(W, want, capacity, use_front && refined, st, res); if (rc) return rc;
@@ -259,8 +261,8 @@ static int stages_after_front(const agb_desc &d, Workspace &W, const void *d_tex
 	return AGB_OK;
 }
 
-static int scan_device_impl(const agb_desc &d, const void *d_text, uint64_t n, int want, int want_level,
-                            agb_record *d_records, uint64_t capacity, cudaStream_t st, agb_result *res)
+int scan_device_impl(const agb_desc &d, const void *d_text, uint64_t n, int want, int want_level,
+                     agb_record *d_records, uint64_t capacity, cudaStream_t st, agb_result *res, const ShardInfo *sh)
 {
 	if (!res) return AGB_ERR_ARG;
 	memset(res, 0, sizeof *res);
@@ -280,7 +282,8 @@ static int scan_device_impl(const agb_desc &d, const void *d_text, uint64_t n, i
 	if (count_in_front) { rc = ordinals_prepare_blocks(d, W, n, st); if (rc) return rc; }
 	if (use_front) { rc = front_launch(d, W, d_text, n, 0, ~0ull, false, st, count_in_front); if (rc) return rc; }
 	CUDA_TRY(cudaEventRecord(W.e1, st));
-	rc = stages_after_front(d, W, d_text, n, use_front, count_in_front, want, want_level, d_records, capacity, st, res); if (rc) return rc;
+	rc = stages_after_front(d, W, d_text, n, use_front, count_in_front, want, want_level, d_records, capacity, st, res, sh); if (rc) return rc;
+	if (sh && W.h_totals[11]) { snprintf(g_err, sizeof g_err, "a record of this shard runs past its halo (%d bytes behind the shard)", AGB_HALO_RIGHT); return AGB_ERR_ARG; }
 	CUDA_TRY(cudaEventElapsedTime(&res->ms_front, W.e0, W.e1));
 	CUDA_TRY(cudaEventElapsedTime(&res->ms_records, W.e1, W.e2));
 	return AGB_OK;

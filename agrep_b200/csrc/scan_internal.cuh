@@ -87,7 +87,13 @@ struct RecParams {
 	int levels;                  /* 1: best-match bookkeeping (smallest matching row) */
 	int want_level;              /* levels: report records whose smallest level <= want_level (-1: all matching) */
 	int warm;                    /* slices form: bytes of warm-up before a slice (>= positions + rows) */
+	/* a shard of a larger text (agb_scan_sharded): the scanned bytes include a halo on either side, and a record belongs
+	 * to the shard whose own range [own_lo, own_hi) holds the last byte of the delimiter that OPENED it (the re-fed byte,
+	 * asearch.c:175-196); unsharded: everything.  shard_last = 0: the delimiter appended behind the text (bitap.c:161-165)
+	 * is not the text's own end -- an owned record that only it closes has outrun the halo (totals[11] is raised) */
+	int64_t own_lo, own_hi; int shard_last;
 };
+struct ShardInfo { int64_t own_lo, own_hi; int last; };
 #define DENSE_THREADS 256
 #define DENSE_TILE    32768
 #define DENSE_TAIL    2048
@@ -117,6 +123,16 @@ struct OrdParams {
 	long long j0;                /* 0, or -1 when the text starts with the user's delimiter (bitap.c:151-156) */
 };
 
+/* does the record opened by the delimiter that starts at `begin` belong to this scan (see RecParams.own_lo)?
+ * close_pos: the last byte of the delimiter that closes it */
+__device__ __forceinline__ bool rec_owned(const RecParams &P, int64_t begin, int L, int64_t close_pos)
+{
+	const int64_t oe = begin + L - 1;
+	if (oe < P.own_lo || oe >= P.own_hi) return false;
+	if (!P.shard_last && close_pos >= (int64_t)P.n) P.totals[11] = 1ull;
+	return true;
+}
+
 /* ---- host ---- */
 #define H2D_SLICE   (64ull << 20)      /* bytes per H2D slice of agb_scan_host; a multiple of the 16 KiB stage */
 #define STAGE_BUFS  3
@@ -130,6 +146,7 @@ struct Workspace {               /* grow-only device scratch, one per device */
 	uint64_t *cand = nullptr; uint32_t *cand_counts = nullptr; uint64_t *cand_offsets = nullptr; agb_record *cand_first = nullptr; size_t cand_cap = 0;
 	uint32_t *scan_sums = nullptr; uint64_t *scan_offs = nullptr; size_t scan_cap = 0;
 	uint16_t *ord_blocks = nullptr; size_t ord_blocks_cap = 0;     /* delimiter ends per 512-byte block (AGB_WANT_ORDINALS) */
+	long long ord_j0 = 0;                                          /* -1 when the text starts with the user's delimiter (bitap.c:151-156) */
 	int ord_virt = 0;                                              /* 1: the virtual '\n' closes a record of its own (1-byte '\n' delimiter) */
 	unsigned long long *totals = nullptr;          /* 16 counters */
 	unsigned long long *h_totals = nullptr;        /* pinned */
@@ -144,6 +161,12 @@ struct Workspace {               /* grow-only device scratch, one per device */
 	uint8_t *stage[STAGE_BUFS] = {nullptr, nullptr, nullptr};
 };
 
+/* scan.cu */
+#include <mutex>
+extern Workspace g_ws[64];
+extern std::mutex g_ws_mu;       /* one scan at a time per process (the workspaces are shared scratch) */
+int  scan_device_impl(const agb_desc &d, const void *d_text, uint64_t n, int want, int want_level,
+                      agb_record *d_records, uint64_t capacity, cudaStream_t st, agb_result *res, const ShardInfo *sh = nullptr);
 /* front.cu */
 bool front_usable(const agb_desc &d);
 bool poly_setup(const uint32_t *a, int na, int bits, uint32_t *coef);

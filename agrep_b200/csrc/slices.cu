@@ -71,7 +71,8 @@ k_records_slices(const RecParams P)
 	const bool active = a < limit;
 	const uint32_t steps = !active ? 0u : (uint32_t)((limit - a) < (int64_t)SL_PER ? (limit - a) : (int64_t)SL_PER);
 	const bool overrun = active && tid == SL_THREADS - 1 && tile_end < limit;    /* finish the record that is open at the end of the tile */
-	const bool easy = tile0 > 0 && tile_end + L + 2 < n;
+	/* (a shard's tiles count the plain way only where every record that opens in them is the shard's own) */
+	const bool easy = tile0 > 0 && tile_end + L + 2 < n && tile0 >= P.own_lo && tile_end <= P.own_hi;
 	T RS[NR];
 #pragma unroll
 	for (int r = 0; r < NR; r++) RS[r] = SH.reset[r];
@@ -124,7 +125,7 @@ k_records_slices(const RecParams P)
 			if (!have_begin) { \
 				if (pass == 0) { has_first = true; first_end = end_; _Pragma("unroll") for (int r = 0; r < NR; r++) first_bits[r] = S[r] & C.endpos; } \
 			} else { \
-				const bool counts = (begin + 1 < n) && (begin + 1 <= end_); \
+				const bool counts = (begin + 1 < n) && (begin + 1 <= end_) && rec_owned(P, begin, L, end_ + L - 1); \
 				int level = C.k; bool cond; \
 				if (P.levels) { \
 					level = -1; \
@@ -237,7 +238,7 @@ k_records_slices(const RecParams P)
 					if (s_has[t]) { first_begin = s_last[t]; found = true; break; }
 				}
 				if (found) {                                         /* else: it opened in an earlier tile, whose last thread reports it */
-					const bool counts = (first_begin + 1 < n) && (first_begin + 1 <= first_end);
+					const bool counts = (first_begin + 1 < n) && (first_begin + 1 <= first_end) && rec_owned(P, first_begin, L, first_end + L - 1);
 					int level = C.k; bool cond;
 					if (P.levels) {
 						level = -1;

@@ -1,4 +1,8 @@
-"""Multi-GPU host logic: shard a text by byte range at record boundaries, gather the per-shard match lists.
+"""Multi-GPU: the Python face of the C sharded scan (agb_scan_sharded, agrep_b200/csrc/shard.cu: the cut rule on the
+device, ncclAllGather of headers and match lists) and, below it, a host restatement of the same cut rule that the CPU
+tests use (gloo, world_size 2).
+
+Host logic: shard a text by byte range at record boundaries, gather the per-shard match lists.
 
 Records are independent once their boundaries are known (the automaton is reset at every delimiter,
 asearch.c:175-196), so the scan path needs no data-path collective: rank r scans [cut[r], cut[r+1]) as a text
@@ -70,7 +74,7 @@ def ordinal_base(closes_before, rank, delim=b"\n"):
     return sum(closes_before) - rank * (1 + virt)
 
 
-def gather_records(recs, n_records, base, dist=None, group=None, closes=None, delim=b"\n"):
+def gather_records(recs, n_records, base, dist=None, group=None, closes=None, delim=b"\n", shard_head=None):
     """recs: int64 tensor [cap, 4] of (begin, end, ordinal, level) with shard-local offsets, n_records valid rows.
     Returns on every rank the concatenation over ranks, offsets made global (+ base) -- ordered because shards are.
     closes: this shard's agb_result.n_closes; when given the ordinals are made global too (an exclusive
@@ -79,6 +83,11 @@ def gather_records(recs, n_records, base, dist=None, group=None, closes=None, de
     blk = recs[:n_records].clone()
     if n_records:
         blk[:, 0:2] += base
+        # a scan reports begin = 0 for its first record when the text has a user delimiter that has not been seen yet; in
+        # the whole text that record was opened by the delimiter that ends just before the shard (begin = base - L) --
+        # unless the shard itself starts with a delimiter, then begin = 0 is that one (the first, empty record is never reported)
+        if base > 0 and bytes(delim) != b"\n" and int(recs[0, 0]) == 0 and not (shard_head is not None and bytes(shard_head[:len(delim)]) == bytes(delim)):
+            blk[0, 0] = base - len(delim)
     if dist is None or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return blk
     world = dist.get_world_size(group)
@@ -98,3 +107,78 @@ def gather_records(recs, n_records, base, dist=None, group=None, closes=None, de
     out = torch.empty((world * m, 4), dtype=torch.int64, device=recs.device)
     dist.all_gather_into_tensor(out, pad, group=group)
     return torch.cat([out[r * m:r * m + counts[r]] for r in range(world)], dim=0)
+
+
+# ---- the C path: one rank per GPU, NCCL inside libagrepb200.so -----------------------------------------------------
+import ctypes as _C
+from . import _lib as _L
+
+
+class Comm:
+    """agb_comm: an NCCL communicator owned by the library.  The 128-byte unique id is made on rank 0 and handed to the
+    other ranks through whatever the caller already has (here: torch.distributed, any backend)."""
+
+    def __init__(self, dist=None, world=None, rank=None, unique_id=None):
+        lib = _L.lib()
+        if dist is not None and dist.is_initialized():
+            world, rank = dist.get_world_size(), dist.get_rank()
+            box = [None]
+            if rank == 0:
+                buf = (_C.c_ubyte * 128)()
+                if lib.agb_comm_unique_id(buf) != 0:
+                    raise RuntimeError(lib.agb_last_error().decode())
+                box[0] = bytes(buf)
+            dist.broadcast_object_list(box, src=0)
+            unique_id = box[0]
+        elif unique_id is None:
+            world, rank = 1, 0
+            buf = (_C.c_ubyte * 128)()
+            if lib.agb_comm_unique_id(buf) != 0:
+                raise RuntimeError(lib.agb_last_error().decode())
+            unique_id = bytes(buf)
+        self.world, self.rank = world, rank
+        self._h = _C.c_void_p()
+        idbuf = (_C.c_ubyte * 128).from_buffer_copy(unique_id)
+        if lib.agb_comm_init(_C.byref(self._h), world, rank, idbuf) != 0:
+            raise RuntimeError(lib.agb_last_error().decode())
+
+    def halo(self, shard_ptr, n_local, stream=0):
+        """fetch the halos of this rank's shard from its neighbours (once per text)"""
+        if _L.lib().agb_shard_halo(self._h, _C.c_void_p(shard_ptr), n_local, _C.c_void_p(stream)) != 0:
+            raise RuntimeError(_L.lib().agb_last_error().decode())
+
+    def scan(self, pattern, shard_ptr, n_local, global_offset, d_records=0, capacity=0, stream=0, ordinals=False, levels=False):
+        want = (_L.WANT_RECORDS if capacity else _L.WANT_COUNT) | (_L.WANT_ORDINALS if ordinals else 0) | (_L.WANT_LEVELS if levels else 0)
+        res = _L.Result()
+        rc = _L.lib().agb_scan_sharded(pattern._h, self._h, _C.c_void_p(shard_ptr), n_local, global_offset, want,
+                                       _C.c_void_p(d_records), capacity, _C.c_void_p(stream), _C.byref(res))
+        if rc != 0:
+            raise RuntimeError("agb_scan_sharded rc=%d: %s" % (rc, _L.lib().agb_last_error().decode()))
+        return res
+
+    def bestmatch(self, pattern, shard_ptr, n_local, global_offset, d_records=0, capacity=0, stream=0, **kw):
+        if isinstance(pattern, str):
+            pattern = pattern.encode("latin-1")
+        d = kw.pop("delim", None)
+        if isinstance(d, str):
+            d = d.encode("latin-1")
+        o = _L.Options(delim=d, **{k: int(v) for k, v in kw.items()})
+        res, best, err = _L.Result(), _C.c_int(-1), _C.create_string_buffer(512)
+        rc = _L.lib().agb_bestmatch_sharded(pattern, _C.byref(o), self._h, _C.c_void_p(shard_ptr), n_local, global_offset,
+                                            _C.c_void_p(d_records), capacity, _C.c_void_p(stream), _C.byref(best), _C.byref(res), err, 512)
+        if rc != 0:
+            raise RuntimeError(err.value.decode() or _L.lib().agb_last_error().decode())
+        return best.value, res
+
+    def __del__(self):
+        try:
+            if self._h:
+                _L.lib().agb_comm_free(self._h)
+        except Exception:
+            pass
+
+
+def shard_buffer(torch, n_local, device):
+    """a device buffer with room for both halos around a shard of n_local bytes: (tensor, pointer of the shard itself)"""
+    t = torch.zeros(_L.HALO_LEFT + n_local + _L.HALO_RIGHT + 64, dtype=torch.uint8, device=device)
+    return t, t.data_ptr() + _L.HALO_LEFT

@@ -4,8 +4,9 @@
 One "step" = one pass of the scan path over the whole synthetic corpus:
     agrep -2 'because each' <64 GiB newline-delimited text>      (BASELINE.json configs[1])
 i.e. stage 1 (k_front, the HBM-bound kernel) + stage 2 (k_records) + the ordered list of matching records;
-with N > 1 the 64 GiB are sharded by byte range over the ranks (records never cross a shard: the corpus
-is made of independent 4 KiB pages) and the match lists are gathered with NCCL.
+with N > 1 the 64 GiB are sharded by byte range over the ranks -- cut inside records, at multiples of 512 bytes -- and
+every rank calls agb_scan_sharded(): the cut rule runs on the device, the match lists are gathered with NCCL inside the
+library (C ABI, include/agrep_b200.h).
 
   python bench.py --gpus N --steps K --warmup W            our arm (one rank per GPU under torchrun)
   python bench.py --impl reference ...                      the reference's own CPU scan on the host cores
@@ -204,7 +205,8 @@ def workload_config(n_gpus):
     return {"workload": "agrep -%d '%s' over %.0f GiB synthetic newline-delimited ASCII (BASELINE.json configs[1]%s)"
                         % (K, PATTERN, TOTAL_GIB, "" if n_gpus == 1 else ", sharded as configs[4]"),
             "pattern": PATTERN, "k": K, "records": "newline", "corpus_gib": TOTAL_GIB,
-            "parallelism": "1 GPU" if n_gpus == 1 else "%d byte-range shards, NCCL all_gather of match lists" % n_gpus,
+            "parallelism": "1 GPU" if n_gpus == 1 else ("%d byte-range shards cut inside records (512-byte multiples), cut rule on the device, "
+                                                           "ncclAllGather of 256-byte headers + match lists inside libagrepb200.so (agb_scan_sharded)" % n_gpus),
             "l2": "input per GPU is far larger than the 126 MB L2; no flush needed",
             "output": "count + ordered (begin,end) list of matching records"}
 
@@ -365,27 +367,54 @@ def main():
     dev = torch.device("cuda", local)
 
     total = int(TOTAL_GIB * (1 << 30)) // (PAGE * world) * (PAGE * world)
-    n_local = total // world
-    first_page = rank * (n_local // PAGE)
-    corpus = torch.empty(n_local + 4096, dtype=torch.uint8, device=dev)
-    corpus[n_local:].zero_()
+    per = total // world
+    # The shards: cut at multiples of 512 bytes that are NOT record boundaries (the corpus is made of independent 4 KiB
+    # pages; a cut 1536 bytes into a page falls inside a line), so that the device-side cut rule of the sharded scan
+    # (a record belongs to the shard that holds the last byte of the delimiter that opened it) is what decides.
+    SKEW = 1536
+    cut = lambda r: 0 if r == 0 else (total if r == world else r * per + SKEW)
+    off, n_local = cut(rank), cut(rank + 1) - cut(rank)
+    HL, HR = _lib.HALO_LEFT, _lib.HALO_RIGHT
+    lead = off - rank * per                                     # bytes of the page-aligned range in front of the shard (0 or SKEW)
+    pages = (lead + n_local + PAGE - 1) // PAGE
+    buf = torch.empty(max(lead, HL) - lead + pages * PAGE + HR + 4096, dtype=torch.uint8, device=dev)
+    gen0 = max(lead, HL) - lead                                  # where the generated pages start inside buf
     stream = torch.cuda.current_stream().cuda_stream
-    ag.corpus_device(corpus.data_ptr(), n_local, stream=stream, first_page=first_page, needle=PATTERN,
+    ag.corpus_device(buf.data_ptr() + gen0, pages * PAGE, stream=stream, first_page=rank * (per // PAGE), needle=PATTERN,
                      needle_every=NEEDLE_EVERY, needle_maxedits=3)
+    buf[gen0 + lead + n_local:].zero_()
     torch.cuda.synchronize()
+    shard_ptr = buf.data_ptr() + gen0 + lead                     # 16-byte aligned: torch allocations are, gen0 + lead is a multiple of 512
+    assert shard_ptr % 16 == 0
+    corpus = buf[gen0 + lead:]                                   # the shard as a tensor (N = 1: the whole corpus)
 
     pat = ag.Pattern(PATTERN, k=K)
     CAP = 1 << 22
     recs = torch.zeros((CAP, 4), dtype=torch.int64, device=dev)       # agb_record = 4 x int64 (level+pad packed in the last)
+    comm = None
+    if world > 1:
+        comm = shard.Comm(dist)                                  # NCCL communicator inside libagrepb200.so (the unique id travels over torch.distributed)
+        comm.halo(shard_ptr, n_local, stream=stream)             # once per text: 64.5 KiB from each neighbour
 
     def step():
-        res = pat.scan_device(corpus.data_ptr(), n_local, stream=stream, d_records=recs.data_ptr(), capacity=CAP)
-        gathered = res.n_records
-        if world > 1:
-            # shard-local offsets -> corpus offsets, then NCCL: all_gather of the counts + all_gather of the padded lists
-            allr = shard.gather_records(recs, int(res.n_records), rank * n_local, dist)
-            gathered = int(allr.shape[0])
-        return res, gathered
+        if world == 1:
+            res = pat.scan_device(shard_ptr, n_local, stream=stream, d_records=recs.data_ptr(), capacity=CAP)
+        else:
+            # every rank scans its shard (cut rule on the device), then ncclAllGather of the headers and of the match lists:
+            # the ordered list of the whole corpus ends up in recs on every rank (agb_scan_sharded, csrc/shard.cu)
+            res = comm.scan(pat, shard_ptr, n_local, off, d_records=recs.data_ptr(), capacity=CAP, stream=stream)
+        if res.truncated:
+            raise SystemExit("the record list did not fit")
+        return res, int(res.n_records)
+
+    if world > 1:
+        # the sharded answer against the same corpus cut at page boundaries (where no record is cut): same total
+        r0 = pat.scan_device(buf.data_ptr() + gen0, per, stream=stream)
+        tt = torch.tensor([int(r0.n_matched)], dtype=torch.int64, device=dev)
+        dist.all_reduce(tt)
+        rs, _ = step()
+        if int(tt.item()) != int(rs.n_matched):
+            raise SystemExit("PARITY FAILURE: sharded scan counted %d records, the page-aligned scans %d" % (rs.n_matched, int(tt.item())))
 
     for _ in range(args.warmup):
         res, gathered = step()
@@ -416,7 +445,7 @@ def main():
     matched_total = gathered
 
     # ---- end to end through the host-buffer entry point (pinned host memory, H2D + result D2H inside the timing)
-    n_e2e = min(int(E2E_GIB * (1 << 30)), n_local) // PAGE * PAGE
+    n_e2e = min(int(E2E_GIB * (1 << 30)), n_local - HR) // PAGE * PAGE
     host = torch.empty(n_e2e, dtype=torch.uint8, pin_memory=True)
     host.copy_(corpus[:n_e2e])
     torch.cuda.synchronize()

@@ -159,6 +159,48 @@ const void *agb_text_device(const agb_text *t);
 /* as agb_scan_device over the resident text, the record list delivered to HOST memory */
 int  agb_scan_text(const agb_pattern *p, const agb_text *t, int want, agb_record *records, uint64_t capacity, agb_result *res);
 
+/* ---- one text over several GPUs: one process per GPU, the text sharded by byte range, NCCL only to gather ----
+ * Records are independent once their boundaries are known (the automaton is reset at every delimiter, asearch.c:175-196),
+ * so a rank scans its shard on its own.  The cut rule runs on the device: a record belongs to the shard that
+ * holds the last byte of the delimiter that opened it; the shard's scan starts AGB_HALO_LEFT bytes before the shard (so
+ * that a delimiter, or a run of "$$", that straddles the cut is parsed as in the whole text) and runs into the next
+ * shard's first AGB_HALO_RIGHT bytes to finish the record in progress.  agb_shard_halo() fetches both halos from the
+ * neighbours (ncclSend/ncclRecv of 64.5 KiB); the caller's buffer has room for them in front of and behind the shard.
+ *
+ *   buffer layout on every rank:   [ AGB_HALO_LEFT | shard: n_local bytes | AGB_HALO_RIGHT + 16 ]
+ *                                                   ^ d_shard, 16-byte aligned; n_local a multiple of 512 on every rank but the last
+ *
+ * agb_scan_sharded: every rank ends up with the same result -- counts summed over the ranks, offsets and ordinals of the
+ * whole text, the ordered list of ALL ranks' records in d_records (ncclAllGather of a 128-byte header per rank, then of the
+ * lists padded to the longest).  global_offset: where this shard starts in the whole text. */
+#define AGB_HALO_LEFT  512
+#define AGB_HALO_RIGHT 65536
+typedef struct agb_comm agb_comm;
+int  agb_comm_unique_id(void *id128);                        /* rank 0: ncclGetUniqueId (128 bytes), to be handed to every rank */
+int  agb_comm_init(agb_comm **out, int world, int rank, const void *id128);   /* on the current device */
+void agb_comm_free(agb_comm *c);
+int  agb_comm_world(const agb_comm *c);
+int  agb_comm_rank(const agb_comm *c);
+int  agb_shard_halo(agb_comm *c, void *d_shard, uint64_t n_local, void *stream);
+int  agb_scan_sharded(const agb_pattern *p, agb_comm *c, const void *d_shard, uint64_t n_local, uint64_t global_offset,
+                      int want, agb_record *d_records, uint64_t capacity, void *stream, agb_result *res);
+/* the local half of agb_scan_sharded, for callers that move the lists themselves (and for one process that walks the
+ * shards of a text one after the other): scans [d_shard - halo_left, d_shard + n_local + halo_right) and keeps the
+ * records the cut rule gives to this shard.  first: nothing precedes the shard; open_end: the shard owns everything up
+ * to the end of what is scanned; reaches_end: the scanned bytes end where the whole text ends.  Offsets and ordinals
+ * in d_records are local to the scanned range; part says how to make them global:
+ *   begin/end += byte_base + (offset of the shard in the whole text);
+ *   ordinal   += ord_origin of the first shard + the closes of all shards before this one - ord_fix. */
+typedef struct agb_shard_part { uint64_t closes; int64_t ord_fix, ord_origin, byte_base; int32_t virt, pad; } agb_shard_part;
+int  agb_scan_shard_local(const agb_pattern *p, const void *d_shard, uint64_t n_local, uint64_t halo_left, uint64_t halo_right,
+                          int first, int open_end, int reaches_end, int want, agb_record *d_records, uint64_t capacity,
+                          void *stream, agb_result *res, agb_shard_part *part);
+/* the -B sweep over the sharded text: the level histograms are summed over the ranks (they ride in the header), every rank
+ * keeps the records of the best level of the WHOLE text, then the gather */
+int  agb_bestmatch_sharded(const char *pattern, const agb_options *opt, agb_comm *c, const void *d_shard, uint64_t n_local,
+                           uint64_t global_offset, agb_record *d_records, uint64_t capacity, void *stream,
+                           int *best_k, agb_result *res, char *err, size_t errlen);
+
 /* j of every record in `records` (ordered, as returned by a scan of h_text[0..n)): the number of record closes
  * up to and including its own (bitap.c:178), with the file-starts-with-the-delimiter correction of bitap.c:151-156.
  * A host walk over the delimiters, only needed for -n. */

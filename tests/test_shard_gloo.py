@@ -25,7 +25,7 @@ def _worker(rank, world, port, text, pattern, kw, delim_bytes, q):
         t = torch.zeros((max(cnt, 1), 4), dtype=torch.int64)
         for i, (b, e, j) in enumerate(recs):
             t[i, 0], t[i, 1], t[i, 2] = b, e, j
-        allr = shard.gather_records(t, cnt, cuts[rank], dist, closes=shard.count_closes(part, delim_bytes), delim=delim_bytes)
+        allr = shard.gather_records(t, cnt, cuts[rank], dist, closes=shard.count_closes(part, delim_bytes), delim=delim_bytes, shard_head=part[:8])
         total = torch.tensor([cnt]); dist.all_reduce(total)
         if rank == 0:
             q.put((int(total), [(int(x[0]), int(x[1]), int(x[2])) for x in allr]))
@@ -68,6 +68,17 @@ def test_paragraph_shards():
     assert total == cnt
     assert [e for _, e, _ in got] == [e for _, e, _ in recs]   # record ends are global; begins differ by the leading delimiter
     assert [j for _, _, j in got] == [j for _, _, j in recs]
+
+
+def test_user_delimiter_seams_keep_the_opening_delimiter():
+    """with -d the record after a cut begins at the delimiter that closed the record before it, as in the whole text"""
+    text = _corpus.make_text(1200, seed=24).replace(b"\n", b"; ")
+    kw = dict(k=1, linenum=1, delim="; ")
+    a = _oracle.compile("people", **kw)
+    cnt, recs = _oracle.scan(a, text)
+    total, got = run_world(2, text, "people", kw, b"; ")
+    assert total == cnt and cnt > 5
+    assert [(b, e) for b, e, _ in got] == [(b, e) for b, e, _ in recs]
 
 
 def test_cut_points_are_record_aligned():
