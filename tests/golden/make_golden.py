@@ -16,17 +16,17 @@ CORPORA = {
 
 # (name, corpus, pattern, reference args (without -V0/-c/-n), api kwargs for oracle/product)
 SCAN_CASES = [
-    ("exact_n", "nl", "because each", ["-n"], dict(k=0, linenum=1)),
-    ("k1", "nl", "because each", ["-n", "-1"], dict(k=1, linenum=1)),
+    ("exact_n", "nl", "against three", ["-n"], dict(k=0, linenum=1)),
+    ("k1", "nl", "against three", ["-n", "-1"], dict(k=1, linenum=1)),
     ("k2", "nl", "because each", ["-n", "-2"], dict(k=2, linenum=1)),
-    ("k2_nonl", "nonl", "because each", ["-n", "-2"], dict(k=2, linenum=1)),
+    ("k2_nonl", "nonl", "also should", ["-n", "-2"], dict(k=2, linenum=1)),
     ("k3", "nl", "government", ["-n", "-3"], dict(k=3, linenum=1)),
     ("k4_i", "nl", "governmental", ["-n", "-4", "-i"], dict(k=4, linenum=1, nocase=1)),
     ("k5", "nl", "governmental", ["-n", "-5"], dict(k=5, linenum=1)),
     ("k8", "nl", "homogeneous approx", ["-n", "-8"], dict(k=8, linenum=1)),
     ("k1_w", "nl", "matching", ["-n", "-1", "-w"], dict(k=1, linenum=1, wordbound=1)),
     ("k0_w", "nl", "the", ["-n", "-w"], dict(k=0, linenum=1, wordbound=1)),
-    ("k2_v", "nl", "pattern string", ["-n", "-2", "-v"], dict(k=2, linenum=1, inverse=1)),
+    ("k2_v", "nl", "the", ["-n", "-1", "-v"], dict(k=1, linenum=1, inverse=1)),
     ("class_k1", "nl", "pat[a-t]ern", ["-n", "-1"], dict(k=1, linenum=1)),
     ("dot", "nl", "st.ing", ["-n"], dict(k=0, linenum=1)),
     ("angle_k2", "nl", "<algo>rithm", ["-n", "-2"], dict(k=2, linenum=1)),
@@ -34,16 +34,16 @@ SCAN_CASES = [
     ("eol_k1", "nl", "world$", ["-n", "-1"], dict(k=1, linenum=1)),
     ("and", "nl", "state;world", ["-n"], dict(k=0, linenum=1)),
     ("negclass", "nl", "[^a-s]he ", ["-n"], dict(k=0, linenum=1)),
-    ("cost_s1", "nl", "between both life", ["-n", "-2", "-S1"], dict(k=2, linenum=1, cost_s=1)),
-    ("cost_s2", "nl", "between both life", ["-n", "-3", "-S2"], dict(k=3, linenum=1, cost_s=2)),
-    ("cost_i2d3", "nl", "between both life", ["-n", "-3", "-I2", "-D3"], dict(k=3, linenum=1, cost_i=2, cost_d=3)),
+    ("cost_s1", "nl", "the other", ["-n", "-2", "-S1"], dict(k=2, linenum=1, cost_s=1)),
+    ("cost_s2", "nl", "of the other", ["-n", "-3", "-S2"], dict(k=3, linenum=1, cost_s=2)),
+    ("cost_i2d3", "nl", "of the other", ["-n", "-3", "-I2", "-D3"], dict(k=3, linenum=1, cost_i=2, cost_d=3)),
     ("insfree", "nl", "government", ["-n", "-2", "-p"], dict(k=2, linenum=1, ins_free=1)),
     ("wild", "nl", "a#t", ["-n"], dict(k=0, linenum=1)),
-    ("i_k0", "nl", "The World", ["-n", "-i"], dict(k=0, linenum=1, nocase=1)),
+    ("i_k0", "nl", "Against Three", ["-n", "-i"], dict(k=0, linenum=1, nocase=1)),
     ("x_k0", "para", "", ["-n", "-x"], None),  # placeholder, removed below
-    ("para_w_k0", "para", "win", ["-n", "-w", "-d", "$$"], dict(k=0, linenum=1, wordbound=1, delim="$$")),
+    ("para_w_k0", "para", "world", ["-n", "-w", "-d", "$$"], dict(k=0, linenum=1, wordbound=1, delim="$$")),
     ("para_w_k2", "para", "because each", ["-n", "-w", "-d", "$$", "-2"], dict(k=2, linenum=1, wordbound=1, delim="$$")),
-    ("para_k3_26", "para", "people how too little stat", ["-n", "-w", "-d", "$$", "-3"],
+    ("para_k3_26", "para", "well eaxh into him here no", ["-n", "-w", "-d", "$$", "-3"],
      dict(k=3, linenum=1, wordbound=1, delim="$$")),
     ("delim_word", "nl", "world", ["-n", "-d", "the", "-1"], dict(k=1, linenum=1, delim="the")),
     # sgrep()/bm() path (config 1)
