@@ -3,6 +3,42 @@
 #include "automaton.cuh"
 #include "corpus.h"
 
+/* how often does each candidate gram of the pattern start in a chunk?  One thread per 16-byte chunk of a sample of
+ * the text (nblk stretches of blk_chunks chunks, evenly spread); the anchor planner (scan.cu) picks the k+1 disjoint
+ * grams with the fewest hits: stage 1.5's work is proportional to the chunks stage 1 flags */
+__global__ void __launch_bounds__(256) k_gram_sample(const uint8_t *text, uint64_t n_chunks, uint32_t nblk, uint32_t blk_chunks,
+                                                    int ngram, const uint32_t *gram, const uint32_t *gmask, uint32_t fold, unsigned int *counts)
+{
+	__shared__ unsigned int s_cnt[128];
+	if (threadIdx.x < 128) s_cnt[threadIdx.x] = 0;
+	__syncthreads();
+	const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint64_t b = t / blk_chunks, i = t % blk_chunks;
+	if (b < nblk) {
+		const uint64_t chunk = (n_chunks / nblk) * b + i;
+		if (chunk + 2 < n_chunks) {
+			const uint4 v = __ldg(reinterpret_cast<const uint4 *>(text) + chunk);
+			const uint32_t x4 = __ldg(reinterpret_cast<const uint32_t *>(text) + (chunk + 1) * 4);
+			const uint32_t x[5] = { v.x | fold, v.y | fold, v.z | fold, v.w | fold, x4 | fold };
+			uint32_t wv[16];
+#pragma unroll
+			for (int w = 0; w < 4; w++) {
+				wv[4 * w] = x[w]; wv[4 * w + 1] = __funnelshift_r(x[w], x[w + 1], 8);
+				wv[4 * w + 2] = __funnelshift_r(x[w], x[w + 1], 16); wv[4 * w + 3] = __funnelshift_r(x[w], x[w + 1], 24);
+			}
+			for (int g = 0; g < ngram; g++) {
+				const uint32_t G = gram[g], M = gmask[g];
+				bool hit = false;
+#pragma unroll
+				for (int s = 0; s < 16; s++) hit = hit || ((wv[s] & M) == G);
+				if (hit) atomicAdd(&s_cnt[g], 1u);
+			}
+		}
+	}
+	__syncthreads();
+	if (threadIdx.x < ngram && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], s_cnt[threadIdx.x]);
+}
+
 /* how dense are the flags?  popcount of every `stride`-th bitmap word (an estimate is all the host needs to pick the
  * record stage's form before it spends time on stage 1.5) */
 __global__ void __launch_bounds__(256) k_bitmap_sample(const uint32_t *bitmap, uint64_t n_words, uint32_t stride, unsigned long long *out)

@@ -218,7 +218,7 @@ enum { S_HYPHEN = 129, S_NOCARE = 130, S_NNLINE = 131, S_WORDB = 133, S_LPAREN =
 static void plan_from_internal(const unsigned char *P, int L, int D, agb_desc *d)
 {
 	int lit[80], n = 0, i, seps = 0, A, plen = (int)strlen((const char *)P);
-	d->plan = AGB_PLAN_ALL; d->n_anchors = 0; d->refine = 0;
+	d->plan = AGB_PLAN_ALL; d->n_anchors = 0; d->refine = 0; d->n_anchors3 = 0; d->adaptive = 1;
 	if (INVERSE || I == 0 || wildmask) return;
 	for (i = 0; i < plen && n < 70; i++) {
 		int c = P[i];

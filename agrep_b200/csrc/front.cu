@@ -16,10 +16,31 @@
  * to the compare form when anchors share low-order bytes).  Anchors shorter than 4 bytes: f is scaled by
  * 256^(4-len), which zeroes exactly when the low len bytes agree.
  * !POLY: unsigned min of the differences (VIADDMNMX), one ALU op per window and anchor. */
-template <int NA, bool MASKED, bool POLY>
+template <int NA, bool MASKED, bool POLY, int N3>
 __device__ __forceinline__ uint32_t windows_test(uint32_t lo, uint32_t hi, const FrontParams &P, uint32_t acc)
 {
 	uint32_t w[4] = { lo, __funnelshift_r(lo, hi, 8), __funnelshift_r(lo, hi, 16), __funnelshift_r(lo, hi, 24) };
+	if (POLY && N3 > 0) {
+		/* mixed plan: NA anchors of four bytes and N3 of three (a piece of the pattern that is only three bytes long, or
+		 * whose rare gram is).  Two polynomials -- one product would cut every anchor to its low three bytes -- the second
+		 * scaled by 256 so that it vanishes exactly when the low three bytes agree; one VIMNMX3 per window takes both. */
+#pragma unroll
+		for (int t = 0; t < 4; t++) {
+			uint32_t r = (NA >= 2) ? __viaddmin_u32(w[t], P.coef[NA - 1], 0xFFFFFFFFu) : w[t] * P.one + P.coef[NA - 1];
+#pragma unroll
+			for (int i = NA - 2; i >= 0; i--) r = r * w[t] + P.coef[i];
+			uint32_t q;
+			if (N3 == 1) q = w[t] * P.s256 + P.coef3[0];             /* 256 (w - B): coef3[0] = -256 B; s256: a run-time 256, so that this stays an IMAD (FMA pipe) and does not become a shift-add on the ALU pipe, which the min and funnel shifts already fill */
+			else {
+				q = w[t] * P.one + P.coef3[N3 - 1];
+#pragma unroll
+				for (int i = N3 - 2; i >= 0; i--) q = q * w[t] + P.coef3[i];
+				q *= P.s256;
+			}
+			acc = __vimin3_u32(acc, r, q);
+		}
+		return acc;
+	}
 	if (POLY) {
 		uint32_t f[4];
 #pragma unroll
@@ -47,7 +68,7 @@ __device__ __forceinline__ uint32_t windows_test(uint32_t lo, uint32_t hi, const
 }
 
 /* the FRONT_CH chunks a thread takes from one stage; FULL = no chunk of the stage is near the end of the text */
-template <int NA, bool MASKED, bool FOLD, bool POLY, bool FULL, bool COUNT>
+template <int NA, bool MASKED, bool FOLD, bool POLY, bool FULL, bool COUNT, int N3>
 __device__ __forceinline__ void front_chunks(const FrontParams &P, const uint8_t *st, uint32_t tid, uint32_t lane, uint32_t rem, uint32_t *bm, uint16_t *nlb)
 {
 #pragma unroll
@@ -78,10 +99,10 @@ __device__ __forceinline__ void front_chunks(const FrontParams &P, const uint8_t
 		}
 		if (FOLD) { v.x |= P.fold; v.y |= P.fold; v.z |= P.fold; v.w |= P.fold; x4 |= P.fold; }
 		uint32_t acc = 0xffffffffu;
-		acc = windows_test<NA, MASKED, POLY>(v.x, v.y, P, acc);
-		acc = windows_test<NA, MASKED, POLY>(v.y, v.z, P, acc);
-		acc = windows_test<NA, MASKED, POLY>(v.z, v.w, P, acc);
-		acc = windows_test<NA, MASKED, POLY>(v.w, x4, P, acc);
+		acc = windows_test<NA, MASKED, POLY, N3>(v.x, v.y, P, acc);
+		acc = windows_test<NA, MASKED, POLY, N3>(v.y, v.z, P, acc);
+		acc = windows_test<NA, MASKED, POLY, N3>(v.z, v.w, P, acc);
+		acc = windows_test<NA, MASKED, POLY, N3>(v.w, x4, P, acc);
 		if (FULL) {
 			const uint32_t word = __ballot_sync(0xffffffffu, acc == 0);
 			if (lane == 0) bm[c * (FRONT_THREADS / 32)] = word;
@@ -99,7 +120,7 @@ __device__ __forceinline__ void front_chunks(const FrontParams &P, const uint8_t
  * ring, each completing on its own mbarrier; all 256 threads take 4 chunks per stage from shared memory
  * (LDS.128, conflict-free: a warp reads 512 consecutive bytes), test the 16 windows of each chunk and ballot
  * the 32 verdicts of a warp into one bitmap word.  Every text byte crosses HBM->SM once. */
-template <int NA, bool MASKED, bool FOLD, bool POLY, bool COUNT>
+template <int NA, bool MASKED, bool FOLD, bool POLY, bool COUNT, int N3>
 __global__ void __launch_bounds__(FRONT_THREADS, FRONT_CTAS_PER_SM)
 k_front(const FrontParams P)
 {
@@ -135,35 +156,42 @@ k_front(const FrontParams P)
 		/* full = every chunk of the stage exists and none is among the last two of the text: no per-chunk EOF logic */
 		const bool full = left >= FRONT_STAGE_CHUNKS + 2;
 		uint16_t *nlb = COUNT ? P.nl_blocks + sg * FRONT_WORDS_PER_STAGE + warp_in_cta : nullptr;
-		if (full) front_chunks<NA, MASKED, FOLD, POLY, true, COUNT>(P, st, tid, lane, rem, bm, nlb);
-		else front_chunks<NA, MASKED, FOLD, POLY, false, COUNT>(P, st, tid, lane, rem, bm, nlb);
+		if (full) front_chunks<NA, MASKED, FOLD, POLY, true, COUNT, N3>(P, st, tid, lane, rem, bm, nlb);
+		else front_chunks<NA, MASKED, FOLD, POLY, false, COUNT, N3>(P, st, tid, lane, rem, bm, nlb);
 		__syncthreads();                       /* everyone is done reading this slot */
 		if (tid == 0) issue((uint64_t)it + FRONT_NST);   /* refill it with the stage FRONT_NST iterations ahead */
 	}
 }
 
-template <int NA, bool MASKED, bool FOLD, bool POLY, bool COUNT>
+template <int NA, bool MASKED, bool FOLD, bool POLY, bool COUNT, int N3>
 static void launch_front_cnt(const FrontParams &P, unsigned grid, cudaStream_t st)
 {
 	static bool configured[64] = {false};
 	int dev = 0; cudaGetDevice(&dev);
 	if (!configured[dev & 63]) {
-		cudaFuncSetAttribute(k_front<NA, MASKED, FOLD, POLY, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FRONT_SMEM);
+		cudaFuncSetAttribute(k_front<NA, MASKED, FOLD, POLY, COUNT, N3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FRONT_SMEM);
 		configured[dev & 63] = true;
 	}
-	k_front<NA, MASKED, FOLD, POLY, COUNT><<<grid, FRONT_THREADS, FRONT_SMEM, st>>>(P);
+	k_front<NA, MASKED, FOLD, POLY, COUNT, N3><<<grid, FRONT_THREADS, FRONT_SMEM, st>>>(P);
 }
-template <int NA, bool MASKED, bool FOLD, bool POLY>
+template <int NA, bool MASKED, bool FOLD, bool POLY, int N3>
 static void launch_front_one(const FrontParams &P, unsigned grid, cudaStream_t st)
 {
-	if (P.nl_blocks) launch_front_cnt<NA, MASKED, FOLD, POLY, true>(P, grid, st);
-	else launch_front_cnt<NA, MASKED, FOLD, POLY, false>(P, grid, st);
+	if (P.nl_blocks) launch_front_cnt<NA, MASKED, FOLD, POLY, true, N3>(P, grid, st);
+	else launch_front_cnt<NA, MASKED, FOLD, POLY, false, N3>(P, grid, st);
 }
 template <int NA, bool POLY>
 static void launch_front_na(const FrontParams &P, bool masked, bool fold, unsigned grid, cudaStream_t st)
 {
-	if (masked) { if (fold) launch_front_one<NA, true, true, POLY>(P, grid, st); else launch_front_one<NA, true, false, POLY>(P, grid, st); }
-	else        { if (fold) launch_front_one<NA, false, true, POLY>(P, grid, st); else launch_front_one<NA, false, false, POLY>(P, grid, st); }
+	if (masked) { if (fold) launch_front_one<NA, true, true, POLY, 0>(P, grid, st); else launch_front_one<NA, true, false, POLY, 0>(P, grid, st); }
+	else        { if (fold) launch_front_one<NA, false, true, POLY, 0>(P, grid, st); else launch_front_one<NA, false, false, POLY, 0>(P, grid, st); }
+}
+/* mixed plans: four-byte anchors by the polynomial + one or two three-byte anchors */
+template <int NA>
+static void launch_front_mixed(const FrontParams &P, bool fold, unsigned grid, cudaStream_t st)
+{
+	if (P.n3 == 1) { if (fold) launch_front_one<NA, false, true, true, 1>(P, grid, st); else launch_front_one<NA, false, false, true, 1>(P, grid, st); }
+	else           { if (fold) launch_front_one<NA, false, true, true, 2>(P, grid, st); else launch_front_one<NA, false, false, true, 2>(P, grid, st); }
 }
 
 /* coefficients of prod_i (x - a_i) mod 2^32 and the false-positive guard of the polynomial form:
@@ -184,7 +212,11 @@ bool poly_setup(const uint32_t *a, int na, int bits, uint32_t *coef)
 	return bits - (na - 1) * t >= 20;
 }
 
-bool front_usable(const agb_desc &d) { return d.plan == AGB_PLAN_ANCHORS && d.n_anchors >= 1 && d.n_anchors <= 9; }
+bool front_usable(const agb_desc &d)
+{
+	if (d.plan != AGB_PLAN_ANCHORS || d.n_anchors < 1 || d.n_anchors > 9) return false;
+	return d.n_anchors3 == 0 || (d.n_anchors3 <= 2 && d.anchor_len == 4 && d.n_anchors <= 7);
+}
 
 /* stage 1 over bitmap words [word_begin, word_end) of a text of n bytes; word_begin must be a multiple of 32
  * (a stage is 32 words).  slack16: 16 more bytes after the last chunk are readable (true for our own buffers). */
@@ -212,9 +244,36 @@ int front_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n
 		for (int j = 0; j < na; j++) if (F.anchor[j] == d.anchor[i]) dup = true;
 		if (!dup) F.anchor[na++] = d.anchor[i];
 	}
-	F.one = 1; F.scale = 1;
+	F.one = 1; F.scale = 1; F.s256 = 256;
 	for (int i = d.anchor_len; i < 4; i++) F.scale <<= 8;
-	const bool poly = poly_setup(F.anchor, na, 8 * d.anchor_len, F.coef);
+	bool poly = poly_setup(F.anchor, na, 8 * d.anchor_len, F.coef);
+	if (d.n_anchors3 > 0) {
+		/* mixed plan: the second polynomial over the three-byte anchors; if either guard fails the three-byte anchors join
+		 * the compare form as four-byte... no such form: fall back to flagging on the four-byte group alone is NOT allowed
+		 * (it would lose matches), so the compare form below gets the 3-byte anchors through their own mask */
+		int n3 = 0; uint32_t a3[4];
+		for (int i = 0; i < d.n_anchors3; i++) {
+			bool dup = false;
+			for (int j = 0; j < n3; j++) if (a3[j] == d.anchor3[i]) dup = true;
+			if (!dup) a3[n3++] = d.anchor3[i];
+		}
+		uint32_t c3[AGB_MAXANCHOR];
+		const bool poly3 = poly_setup(a3, n3, 24, c3);
+		if (!(poly && poly3)) { snprintf(g_err, sizeof g_err, "internal: mixed anchor plan without a polynomial form"); return AGB_ERR_ARG; }
+		F.n3 = n3;
+		for (int i = 0; i < n3; i++) F.coef3[i] = c3[i];
+		if (n3 == 1) F.coef3[0] = 0u - 256u * a3[0];
+		switch (na) {
+		case 1: launch_front_mixed<1>(F, fold, grid, st); break;  case 2: launch_front_mixed<2>(F, fold, grid, st); break;
+		case 3: launch_front_mixed<3>(F, fold, grid, st); break;  case 4: launch_front_mixed<4>(F, fold, grid, st); break;
+		case 5: launch_front_mixed<5>(F, fold, grid, st); break;  case 6: launch_front_mixed<6>(F, fold, grid, st); break;
+		case 7: launch_front_mixed<7>(F, fold, grid, st); break;
+		default: return AGB_ERR_ARG;
+		}
+		g_launches++;
+		CUDA_TRY(cudaGetLastError());
+		return AGB_OK;
+	}
 #define FRONT_CASE(N) case N: if (poly) launch_front_na<N, true>(F, masked, fold, grid, st); else launch_front_na<N, false>(F, masked, fold, grid, st); break;
 	switch (na) {
 	FRONT_CASE(1) FRONT_CASE(2) FRONT_CASE(3) FRONT_CASE(4) FRONT_CASE(5) FRONT_CASE(6) FRONT_CASE(7) FRONT_CASE(8) FRONT_CASE(9)

@@ -353,7 +353,7 @@ static int collect_runs(const build_t *b, int part, int A, int ascii_only, uint3
 static void plan_anchors(const build_t *b, agb_desc *d, const agb_options *o, int fold_all)
 {
 	int A, p, part;
-	d->plan = AGB_PLAN_ALL; d->n_anchors = 0;
+	d->plan = AGB_PLAN_ALL; d->n_anchors = 0; d->n_anchors3 = 0; d->adaptive = 1;
 	if (d->inverse || o->ins_free) return;   /* -v reports the NON-matching records; -p makes insertions free */
 	for (A = 4; A >= 2; A--) {
 		uint32_t got[AGB_MAXANCHOR]; int pos[AGB_MAXANCHOR], ngot = 0, ok = 1;
@@ -539,6 +539,7 @@ int agb_pattern_from_desc(const agb_desc *d, agb_pattern **out, char *err, size_
 	if (p->d.plan != AGB_PLAN_ANCHORS || p->d.n_anchors < 1 || p->d.n_anchors > AGB_MAXANCHOR || p->d.anchor_len < 2 || p->d.anchor_len > 4) {
 		p->d.plan = AGB_PLAN_ALL; p->d.n_anchors = 0; p->d.refine = 0;
 	}
+	if (p->d.n_anchors3 < 0 || p->d.n_anchors3 > 2 || p->d.plan != AGB_PLAN_ANCHORS) p->d.n_anchors3 = 0;
 	rc = agbi_derive(&p->d, err, errlen);
 	if (rc) { free(p); *out = NULL; return rc; }
 	*out = p;

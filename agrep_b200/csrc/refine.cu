@@ -75,6 +75,7 @@ static bool refine_geometry(const agb_desc &d, RefineParams &P)
 	if (!front_usable(d) || !d.refine) return false;
 	int max_off = 0, min_off = 1 << 30;
 	for (int i = 0; i < d.n_anchors; i++) { max_off = std::max(max_off, (int)d.anchor_off[i]); min_off = std::min(min_off, (int)d.anchor_off[i]); }
+	for (int i = 0; i < d.n_anchors3; i++) { max_off = std::max(max_off, (int)d.anchor3_off[i]); min_off = std::min(min_off, (int)d.anchor3_off[i]); }
 	P.lo_off = max_off + d.k;
 	P.hi_off = 15 + d.pat_len - min_off + d.k;
 	P.gb = (P.lo_off + 15) / 16;
@@ -83,20 +84,27 @@ static bool refine_geometry(const agb_desc &d, RefineParams &P)
 	const int pw = (d.pat_len + 3) / 4, ngc = (d.engine != AGB_ENGINE_ASEARCH1 && d.M <= 31 && pw <= 4) ? 4 : REFINE_MAXG;
 	if (!(P.ng <= ngc && max_off <= 31 && d.pat_len >= 1 && d.pat_len <= 64)) return false;
 	/* which anchor a hit window holds is looked up through a multiplicative hash of its bytes: 32 slots, a multiplier
-	 * that keeps the anchors apart (equal anchors at different offsets, "abab" in "abababab", have no such thing: those
-	 * patterns go to stage 2 unthinned) */
+	 * that keeps the anchors apart.  Equal anchors at different offsets ("abab" in "abababab"), or a three-byte anchor
+	 * that is the head of a four-byte one, have no such thing: those patterns go to stage 2 unthinned. */
+	const int na = d.n_anchors + d.n_anchors3;
+	if (na > 16) return false;
+	uint32_t val[16], msk[16]; int off[16];
+	for (int i = 0; i < d.n_anchors; i++) { val[i] = d.anchor[i]; msk[i] = d.anchor_mask; off[i] = d.anchor_off[i]; }
+	for (int i = 0; i < d.n_anchors3; i++) { val[d.n_anchors + i] = d.anchor3[i]; msk[d.n_anchors + i] = 0x00FFFFFFu; off[d.n_anchors + i] = d.anchor3_off[i]; }
+	for (int i = 0; i < na; i++) for (int j = 0; j < i; j++) if ((val[i] & msk[j]) == val[j] || (val[j] & msk[i]) == val[i]) return false;
 	uint32_t mul = 0x9E3779B1u;
 	for (int attempt = 0; attempt < 4096; attempt++, mul = mul * 0x2C1B3C6Du + 0x297A2D39u) {
 		int8_t slot[32]; bool ok = true;
-		memset(slot, -1, sizeof slot);
+		memset(slot, 0, sizeof slot);
 		mul |= 1u;
-		for (int i = 0; i < d.n_anchors && ok; i++) {
-			const uint32_t h = (d.anchor[i] * mul) >> 27;
-			if (slot[h] >= 0) ok = false; else slot[h] = (int8_t)i;
+		for (int i = 0; i < na && ok; i++) {
+			const uint32_t h = (val[i] * mul) >> 27;
+			if (slot[h]) ok = false; else slot[h] = (int8_t)(i + 1);
 		}
 		if (!ok) continue;
 		P.hmul = mul;
-		for (int h = 0; h < 32; h++) P.hoff[h] = slot[h] >= 0 ? (int8_t)d.anchor_off[slot[h]] : 0;
+		memcpy(P.hidx, slot, sizeof slot);
+		for (int i = 0; i < 16; i++) { P.hval[i] = i < na ? val[i] : 0; P.hmask[i] = i < na ? msk[i] : 0; P.hoffs[i] = i < na ? (int8_t)off[i] : 0; }
 		return true;
 	}
 	return false;
@@ -149,6 +157,13 @@ int refine_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t 
 		P.one = 1; P.scale = 1;
 		for (int i = d.anchor_len; i < 4; i++) P.scale <<= 8;
 		P.poly = (distinct && poly_setup(d.anchor, d.n_anchors, 8 * d.anchor_len, P.coef)) ? 1 : 0;
+		P.n3 = 0;
+		if (d.n_anchors3) {
+			uint32_t c3[AGB_MAXANCHOR];
+			if (!P.poly || !poly_setup(d.anchor3, d.n_anchors3, 24, c3)) return AGB_OK;      /* (the planner only makes plans that have both) */
+			P.n3 = d.n_anchors3;
+			for (int i = 0; i < d.n_anchors3; i++) P.coef3[i] = c3[i];
+		}
 	}
 	refine_t1_setup(d, P);
 	unsigned grid = refine_grid(W, n);

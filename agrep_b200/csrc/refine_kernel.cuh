@@ -13,7 +13,7 @@
 /* the hit windows of a chunk: bit s of the result = some anchor starts at byte s.  Stage 1's polynomial over the
  * 16 windows (IMADs on the FMA pipe); f == 0 is folded into a bit per window without a compare: min(f, 1) shifted
  * into the mask by a multiply-add.  x[0..4]: the chunk and the word that follows it, case-folded like stage 1 does. */
-template <int NA, bool SCALED>
+template <int NA, bool SCALED, int N3 = 0>
 __device__ __forceinline__ uint32_t hit_windows_poly(const uint32_t (&x)[5], const RefineParams &P)
 {
 	uint32_t wv[16];
@@ -29,6 +29,12 @@ __device__ __forceinline__ uint32_t hit_windows_poly(const uint32_t (&x)[5], con
 #pragma unroll
 		for (int i = NA - 2; i >= 0; i--) r = r * wv[s] + P.coef[i];
 		if (SCALED) r *= P.scale;
+		if (N3 > 0) {                                        /* mixed plan: the three-byte group's polynomial, scaled by 256 */
+			uint32_t q = wv[s] * P.one + P.coef3[N3 - 1];
+#pragma unroll
+			for (int i = N3 - 2; i >= 0; i--) q = q * wv[s] + P.coef3[i];
+			r = min(r, q * 256u);
+		}
 		nz = nz * 2u + min(r, 1u);
 	}
 	return ~nz & 0xFFFFu;
@@ -59,20 +65,49 @@ __device__ __forceinline__ uint32_t hit_windows_na(const uint32_t (&x)[5], const
 	default: return hit_windows_poly<9, SCALED>(x, P);
 	}
 }
+__device__ __forceinline__ uint32_t hit_windows_mixed(const uint32_t (&x)[5], const RefineParams &P)
+{
+	if (P.n3 == 1) switch (P.na) {
+	case 1: return hit_windows_poly<1, false, 1>(x, P);  case 2: return hit_windows_poly<2, false, 1>(x, P);
+	case 3: return hit_windows_poly<3, false, 1>(x, P);  case 4: return hit_windows_poly<4, false, 1>(x, P);
+	case 5: return hit_windows_poly<5, false, 1>(x, P);  case 6: return hit_windows_poly<6, false, 1>(x, P);
+	default: return hit_windows_poly<7, false, 1>(x, P);
+	}
+	switch (P.na) {
+	case 1: return hit_windows_poly<1, false, 2>(x, P);  case 2: return hit_windows_poly<2, false, 2>(x, P);
+	case 3: return hit_windows_poly<3, false, 2>(x, P);  case 4: return hit_windows_poly<4, false, 2>(x, P);
+	case 5: return hit_windows_poly<5, false, 2>(x, P);  case 6: return hit_windows_poly<6, false, 2>(x, P);
+	default: return hit_windows_poly<7, false, 2>(x, P);
+	}
+}
 __device__ __forceinline__ uint32_t hit_windows(const uint32_t (&x)[5], const RefineParams &P)
 {
+	if (P.n3) return hit_windows_mixed(x, P);
 	if (!P.poly) return hit_windows_cmp(x, P);
 	return P.scale != 1 ? hit_windows_na<true>(x, P) : hit_windows_na<false>(x, P);
 }
 
 /* the pattern start a hit window stands for: code = 32 + s - off of the anchor that starts at byte s of the chunk
- * (p0 = 16 * chunk + code - 32).  cw: the chunk's words in the lane's strip; offs: off of every anchor at the slot a
- * multiplicative hash of its bytes picks (the host found a multiplier that keeps the anchors apart). */
-__device__ __forceinline__ uint32_t start_code(const uint32_t *cw, const int s, const RefineParams &P, const int8_t *offs)
+ * (p0 = 16 * chunk + code - 32).  cw: the chunk's words in the lane's strip.  Which anchor it is: a multiplicative hash
+ * of the window's bytes picks a slot (the host found a multiplier that keeps the anchors apart); the four-byte reading
+ * of the window is tried first, then (mixed plans) the three-byte one. */
+struct AnchorTable { int8_t idx[32]; uint32_t val[16], mask[16]; int8_t off[16]; };
+__device__ __forceinline__ uint32_t start_code(const uint32_t *cw, const int s, const RefineParams &P, const AnchorTable &A)
 {
 	const uint32_t lo = cw[s >> 2] | P.fold, hi = cw[(s >> 2) + 1] | P.fold;
-	const uint32_t v = __funnelshift_r(lo, hi, (s & 3) * 8) & P.amask;
-	return (uint32_t)(32 + s - (int)offs[(v * P.hmul) >> 27]);
+	const uint32_t v = __funnelshift_r(lo, hi, (s & 3) * 8);
+	int off = 0;
+	{
+		const uint32_t v4 = v & P.amask;
+		const int i = A.idx[(v4 * P.hmul) >> 27];
+		if (i && A.val[i - 1] == (v & A.mask[i - 1])) off = A.off[i - 1];
+		else if (P.n3) {
+			const uint32_t v3 = v & 0x00FFFFFFu;
+			const int i3 = A.idx[(v3 * P.hmul) >> 27];
+			if (i3 && A.val[i3 - 1] == (v & A.mask[i3 - 1])) off = A.off[i3 - 1];
+		}
+	}
+	return (uint32_t)(32 + s - off);
 }
 
 /* T1, the band count: the literal pattern positions no byte of whose band matches, for the pattern start whose window
@@ -178,8 +213,9 @@ k_refine(const RefineParams P)
 	__shared__ uint32_t s_ring1[REFINE_THREADS / 32][REFINE_RING1];
 	__shared__ uint32_t s_ring2[REFINE_THREADS / 32][REFINE_RING2];
 	__shared__ uint32_t s_ring3[REFINE_THREADS / 32][REFINE_RING3];
-	__shared__ int8_t s_offs[32];
-	if (threadIdx.x < 32) s_offs[threadIdx.x] = P.hoff[threadIdx.x];
+	__shared__ AnchorTable s_offs;
+	if (threadIdx.x < 32) s_offs.idx[threadIdx.x] = P.hidx[threadIdx.x];
+	if (threadIdx.x < 16) { s_offs.val[threadIdx.x] = P.hval[threadIdx.x]; s_offs.mask[threadIdx.x] = P.hmask[threadIdx.x]; s_offs.off[threadIdx.x] = P.hoffs[threadIdx.x]; }
 	DevConsts<T> C;
 	shared_init<T, NR>(SH, C, P.desc, REFINE_THREADS);
 	const T init0 = mirror<T>((T)P.desc->init0);

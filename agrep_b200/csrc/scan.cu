@@ -232,6 +232,130 @@ static int ordinals_prepare_blocks(const agb_desc &d, Workspace &W, uint64_t n, 
 	return AGB_OK;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * the anchor planner.  Any k+1 disjoint literal grams of the pattern make a valid pigeonhole filter; which ones
+ * decides how many chunks stage 1 flags -- 4.5 % of the benchmark text for beca|use |each, 2.4 % for beca|se e|ach --
+ * and stage 1.5 pays per flagged chunk.  The static plan (pattern.c) takes the first k+1 runs; here, for texts large
+ * enough to care, the candidate grams (every literal 4-gram and 3-gram of the pattern) are counted on a 4 MiB sample
+ * of the text and the cheapest set is chosen by a small dynamic program: four-byte grams, plus up to two three-byte
+ * grams (which cost stage 1 one more operation per window: they only pay when they save enough flags).
+ * Works from the Mask[] words alone, so the drop-in layer's descriptors are re-planned too.
+ * ---------------------------------------------------------------------------------------------- */
+#define PLAN_MIN_BYTES   (256ull << 20)
+#define PLAN_SAMPLE_BLK  64               /* stretches */
+#define PLAN_BLK_CHUNKS  4096             /* of 64 KiB */
+static int adaptive_plan(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, cudaStream_t st, agb_desc *out)
+{
+	*out = d;
+	if (!d.adaptive || !front_usable(d) || !d.refine || d.n_anchors3 || n < PLAN_MIN_BYTES || d.pat_len < 4 || d.pat_len > 60) return AGB_OK;
+	const int need = d.k + 1;
+	if (need > 9) return AGB_OK;
+	uint64_t key = 1469598103934665603ull;
+	{
+		const unsigned char *b = (const unsigned char *)&d;
+		for (size_t i = 0; i < sizeof d; i++) { key ^= b[i]; key *= 1099511628211ull; }
+		key ^= (uint64_t)(uintptr_t)d_text; key *= 1099511628211ull; key ^= n; key *= 1099511628211ull;
+	}
+	if (W.plan_valid && W.plan_key == key) { *out = W.plan_desc; return AGB_OK; }
+	/* literal bytes of the pattern proper, from the masks */
+	int lit[64]; bool pair_any = false;
+	for (int j = 0; j < d.pat_len; j++) {
+		const uint64_t bit = 1ull << (d.M - (d.L + 2 + j));
+		int cnt = 0, c0 = -1, c1 = -1;
+		for (int c = 0; c < 256; c++) if (d.mask[c] & bit) { if (cnt == 0) c0 = c; else if (cnt == 1) c1 = c; cnt++; }
+		lit[j] = -1;
+		if (cnt == 1 && c0 != '\n' && c0 < 0x80) lit[j] = c0;
+		else if (cnt == 2 && (c0 ^ c1) == 0x20 && c1 < 0x80) { lit[j] = c0 | 0x20; pair_any = true; }
+	}
+	const uint32_t fold = pair_any ? 0x20202020u : 0u;
+	/* candidate grams */
+	struct Gram { int s, len; uint32_t v, m; double cost; };
+	Gram g[128]; int ng = 0;
+	for (int len = 4; len >= 3; len--)
+		for (int s = 0; s + len <= d.pat_len && ng < 120; s++) {
+			bool ok = true; uint32_t v = 0;
+			for (int t = 0; t < len; t++) { if (lit[s + t] < 0) ok = false; else v |= (uint32_t)(lit[s + t] | (fold & 0x20)) << (8 * t); }
+			if (!ok) continue;
+			g[ng].s = s; g[ng].len = len; g[ng].v = v; g[ng].m = len == 4 ? 0xFFFFFFFFu : 0x00FFFFFFu; g[ng].cost = 0; ng++;
+		}
+	if (ng < need) return AGB_OK;
+	if (!W.d_gram) { CUDA_TRY(cudaMalloc(&W.d_gram, 3 * 128 * sizeof(uint32_t))); CUDA_TRY(cudaMallocHost(&W.h_gram, 3 * 128 * sizeof(uint32_t))); }
+	for (int i = 0; i < 128; i++) { W.h_gram[i] = i < ng ? g[i].v : 0; W.h_gram[128 + i] = i < ng ? g[i].m : 0; W.h_gram[256 + i] = 0; }
+	CUDA_TRY(cudaMemcpyAsync(W.d_gram, W.h_gram, 3 * 128 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+	const uint64_t n_chunks = (n + 15) / 16;
+	const uint64_t threads = (uint64_t)PLAN_SAMPLE_BLK * PLAN_BLK_CHUNKS;
+	k_gram_sample<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((const uint8_t *)d_text, n_chunks, PLAN_SAMPLE_BLK, PLAN_BLK_CHUNKS,
+	                                                                 ng, W.d_gram, W.d_gram + 128, fold, W.d_gram + 256);
+	g_launches++;
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaMemcpyAsync(W.h_gram + 256, W.d_gram + 256, 128 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	for (int i = 0; i < ng; i++) g[i].cost = (double)W.h_gram[256 + i] / (double)threads;
+	/* dynamic program over the pattern positions: f[p][j][t] = least total rate of j disjoint grams inside [0, p), t of them
+	 * three bytes long */
+	/* what a three-byte group costs, in units of flag rate: measured on the benchmark pattern (beca|se e|ach flags 2.4 %
+	 * of the chunks instead of 4.5 %), stage 1 ran 22 % longer (14.5 instead of 11.8 ms per 64 GiB: the second polynomial
+	 * and one VIMNMX3 per window instead of half of one) and stage 1.5 did not get cheaper in proportion -- a mixed plan
+	 * only pays when the four-byte grams of a piece are really common */
+	const double INF = 1e30, MIXED = 0.03;
+	static double f[66][10][3]; static int from[66][10][3];   /* gram taken to get here, -1: position skipped */
+	for (int p = 0; p <= d.pat_len; p++) for (int j = 0; j <= need; j++) for (int t = 0; t < 3; t++) { f[p][j][t] = INF; from[p][j][t] = -2; }
+	f[0][0][0] = 0;
+	for (int p = 0; p < d.pat_len; p++)
+		for (int j = 0; j <= need; j++) for (int t = 0; t < 3; t++) {
+			if (f[p][j][t] >= INF) continue;
+			if (f[p][j][t] < f[p + 1][j][t]) { f[p + 1][j][t] = f[p][j][t]; from[p + 1][j][t] = -1; }
+			if (j == need) continue;
+			for (int i = 0; i < ng; i++) if (g[i].s == p) {
+				const int t2 = t + (g[i].len == 3), p2 = p + g[i].len;
+				if (t2 > 2) continue;
+				if (f[p][j][t] + g[i].cost < f[p2][j + 1][t2]) { f[p2][j + 1][t2] = f[p][j][t] + g[i].cost; from[p2][j + 1][t2] = i; }
+			}
+		}
+	int best_t = -1; double best = INF;
+	for (int t = 0; t < 3; t++) {
+		if (need - t < 1 || need - t > (t ? 7 : 9)) continue;
+		const double c = f[d.pat_len][need][t] + (t ? MIXED : 0);
+		if (c < best) { best = c; best_t = t; }
+	}
+	double cur = 0;                                     /* the static plan's rate, from the same sample where it can be read off */
+	for (int a = 0; a < d.n_anchors; a++) { double r = 1.0; for (int i = 0; i < ng; i++) if (g[i].len == d.anchor_len && g[i].s == d.anchor_off[a]) r = g[i].cost; cur += r; }
+	if (best_t < 0 || !(best < 0.85 * cur)) { W.plan_key = key; W.plan_valid = true; W.plan_desc = d; return AGB_OK; }
+	agb_desc nd = d;
+	nd.n_anchors = 0; nd.n_anchors3 = 0; nd.anchor_len = 4; nd.anchor_mask = 0xFFFFFFFFu; nd.anchor_fold = fold;
+	{
+		int p = d.pat_len, j = need, t = best_t;
+		while (p > 0 && j >= 0) {
+			const int fr = from[p][j][t];
+			if (fr == -1) { p--; continue; }
+			if (fr < 0) break;
+			if (g[fr].len == 4) { nd.anchor[nd.n_anchors] = g[fr].v; nd.anchor_off[nd.n_anchors] = g[fr].s; nd.n_anchors++; }
+			else { nd.anchor3[nd.n_anchors3] = g[fr].v; nd.anchor3_off[nd.n_anchors3] = g[fr].s; nd.n_anchors3++; }
+			p -= g[fr].len; j--; t -= (g[fr].len == 3);
+		}
+	}
+	/* the kernels want their polynomials: both groups must pass the false-positive guard, and the anchors must be
+	 * pairwise distinct (stage 1.5 tells them apart by their bytes) */
+	bool ok = nd.n_anchors + nd.n_anchors3 == need && nd.n_anchors >= 1;
+	uint32_t tmp[AGB_MAXANCHOR];
+	if (ok) ok = poly_setup(nd.anchor, nd.n_anchors, 32, tmp);
+	if (ok && nd.n_anchors3) ok = poly_setup(nd.anchor3, nd.n_anchors3, 24, tmp);
+	for (int a = 0; a < nd.n_anchors && ok; a++) {
+		for (int b = 0; b < a; b++) if (nd.anchor[a] == nd.anchor[b]) ok = false;
+		for (int b = 0; b < nd.n_anchors3; b++) if ((nd.anchor[a] & 0x00FFFFFFu) == nd.anchor3[b]) ok = false;
+	}
+	for (int a = 0; a < nd.n_anchors3 && ok; a++) for (int b = 0; b < a; b++) if (nd.anchor3[a] == nd.anchor3[b]) ok = false;
+	W.plan_key = key; W.plan_valid = true; W.plan_desc = ok ? nd : d;
+	*out = W.plan_desc;
+	if (getenv("AGB_DEBUG_PLAN")) {
+		fprintf(stderr, "agb plan: static rate %.4f -> %s rate %.4f:", cur, ok ? "chosen" : "rejected", best);
+		for (int a = 0; a < nd.n_anchors; a++) fprintf(stderr, " [%.4s]@%d", (const char *)&nd.anchor[a], nd.anchor_off[a]);
+		for (int a = 0; a < nd.n_anchors3; a++) fprintf(stderr, " [%.3s]@%d", (const char *)&nd.anchor3[a], nd.anchor3_off[a]);
+		fprintf(stderr, "\n");
+	}
+	return AGB_OK;
+}
+
 /* everything after stage 1, on one stream: stage 1.5, the record stage, the ordinals, the result read-back (the one
  * host synchronisation of a scan).  The candidate list of the list form is sized without asking the device how many
  * survivors there are; should it turn out too small (totals[12] > capacity, seen in the read-back) the record stage
@@ -261,7 +385,7 @@ static int stages_after_front(const agb_desc &d, Workspace &W, const void *d_tex
 	return AGB_OK;
 }
 
-int scan_device_impl(const agb_desc &d, const void *d_text, uint64_t n, int want, int want_level,
+int scan_device_impl(const agb_desc &d_in, const void *d_text, uint64_t n, int want, int want_level,
                      agb_record *d_records, uint64_t capacity, cudaStream_t st, agb_result *res, const ShardInfo *sh)
 {
 	if (!res) return AGB_ERR_ARG;
@@ -273,6 +397,9 @@ int scan_device_impl(const agb_desc &d, const void *d_text, uint64_t n, int want
 	std::lock_guard<std::mutex> lk(g_ws_mu);
 	Workspace &W = g_ws[dev];
 	int rc = ws_prepare(W, n); if (rc) return rc;
+	agb_desc planned;
+	rc = adaptive_plan(d_in, W, d_text, n, st, &planned); if (rc) return rc;
+	const agb_desc &d = planned;
 	rc = ws_upload_desc(W, d, st); if (rc) return rc;
 	CUDA_TRY(cudaMemsetAsync(W.totals, 0, 16 * sizeof(unsigned long long), st));
 	CUDA_TRY(cudaEventRecord(W.e0, st));

@@ -47,6 +47,9 @@ struct FrontParams {
 	uint32_t     one, scale;     /* 1 (kept opaque so the first Horner step stays an IMAD) and 256^(4-anchor_len) */
 	uint32_t     anchor[AGB_MAXANCHOR];
 	uint32_t     coef[AGB_MAXANCHOR];   /* prod_i (x - anchor[i]) mod 2^32, low order first, leading 1 implied */
+	int          n3;             /* mixed plan: three-byte anchors, their polynomial (scaled by 256 in the kernel) */
+	uint32_t     s256;
+	uint32_t     coef3[4];
 	uint16_t    *nl_blocks;      /* COUNT: delimiter bytes per 512-byte block = per bitmap word (the ordinals' first pass, fused) */
 	uint32_t     delim4;         /* the 1-byte delimiter, four times */
 };
@@ -65,7 +68,9 @@ struct RefineParams {
 	uint32_t coef[AGB_MAXANCHOR]; uint32_t one, scale; int poly;   /* stage 1's polynomial, to spot the candidate windows cheaply */
 	int t1, t1_words;            /* the band count: usable; words of the window [p0 - k, p0 + pat_len + k) */
 	uint32_t t1_fold, t1_pat[16], t1_care[16];   /* literal pattern bytes (little endian words), 0x80 per literal position */
-	uint32_t hmul; int8_t hoff[32];              /* anchor bytes -> off: slot (bytes * hmul) >> 27 */
+	uint32_t hmul; int8_t hidx[32];              /* anchor bytes -> anchor: slot (bytes * hmul) >> 27 holds its index + 1 */
+	uint32_t hval[16], hmask[16]; int8_t hoffs[16];   /* the anchors of both groups: bytes, mask (4 or 3 bytes), off */
+	int n3; uint32_t coef3[4];                   /* mixed plan: the three-byte group's polynomial */
 	int sm_count;
 };
 
@@ -141,6 +146,9 @@ struct Workspace {               /* grow-only device scratch, one per device */
 	uint32_t *bitmap2 = nullptr;                                    /* stage 1.5: the survivors (same size as bitmap) */
 	uint32_t *range_counts = nullptr; uint64_t *range_offsets = nullptr;   /* per warp range of stage 1.5: survivor counts, their scan */
 	unsigned refine_ctas = 0;                                       /* grid of the last stage 1.5 launch */
+	/* anchor planner: the sample counts of the candidate grams; the plan chosen for the last (descriptor, text) */
+	uint32_t *d_gram = nullptr; unsigned int *h_gram = nullptr;     /* device: 128 grams + 128 masks + 128 counts; pinned: the same */
+	uint64_t plan_key = 0; bool plan_valid = false; agb_desc plan_desc;
 	size_t cand_hint = 0;                                          /* candidates the last scans needed (sizes the list without a host round trip) */
 	uint32_t *tile_counts = nullptr; uint64_t *tile_offsets = nullptr; size_t tiles = 0;
 	uint64_t *cand = nullptr; uint32_t *cand_counts = nullptr; uint64_t *cand_offsets = nullptr; agb_record *cand_first = nullptr; size_t cand_cap = 0;
@@ -183,6 +191,8 @@ int  launch_records_list(const agb_desc &d, const RecParams &P, unsigned grid, c
 int  launch_slices(const agb_desc &d, const RecParams &P, unsigned grid, cudaStream_t st);
 bool slices_usable(const agb_desc &d);
 /* aux.cu */
+__global__ void k_gram_sample(const uint8_t *text, uint64_t n_chunks, uint32_t nblk, uint32_t blk_chunks,
+                              int ngram, const uint32_t *gram, const uint32_t *gmask, uint32_t fold, unsigned int *counts);
 __global__ void k_compact_count(const uint32_t *bitmap, uint64_t n_words, uint32_t *block_counts, unsigned long long *totals);
 __global__ void k_compact_write(const uint32_t *bitmap, uint64_t n_words, const uint64_t *block_offsets, uint64_t *cand, uint64_t cand_cap);
 __global__ void k_scan_tiles(const uint32_t *counts, uint64_t *offsets, uint64_t n_tiles, unsigned long long *total);

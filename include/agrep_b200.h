@@ -88,6 +88,12 @@ typedef struct agb_desc {
 	 * window [p - off - k, p + pat_len - off + k) alone (single pattern, no '#', no -v/-p) */
 	int32_t  refine, pat_len;
 	int32_t  anchor_off[AGB_MAXANCHOR];
+	/* mixed plan: besides the n_anchors anchors of anchor_len = 4 bytes, n_anchors3 pieces of the pattern stand with a
+	 * three-byte gram (the piece is only three bytes long, or that is its rare gram); n_anchors + n_anchors3 = k + 1 */
+	int32_t  n_anchors3;
+	uint32_t anchor3[4];                      /* low three bytes, folded like anchor[] */
+	int32_t  anchor3_off[4];
+	int32_t  adaptive;                        /* 1: the device scan may re-plan the anchors from a sample of the text */
 } agb_desc;
 
 typedef struct agb_pattern agb_pattern;       /* opaque: agb_desc + bookkeeping              */

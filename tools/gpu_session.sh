@@ -1,8 +1,6 @@
 set -x
 cd $GRAFT_REPO_ROOT
-nvidia-smi -L
-timeout 900 python -m pytest tests/test_gpu_shard.py tests/test_gpu_shard_nccl.py -x -q -m gpu 2>&1 | tail -25 > gpurun_out/r2g_tests.log
-tail -25 gpurun_out/r2g_tests.log
-AGB_BENCH_SECONDARY=0 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2g_bench_n2.json 2> gpurun_out/r2g_bench_n2.err
-tail -5 gpurun_out/r2g_bench_n2.err
-cut -c1-900 gpurun_out/r2g_bench_n2.json
+AGB_DEBUG_PLAN=1 timeout 300 python tools/one_scan.py 64 "because each" k=2 list=1 reps=4 > gpurun_out/r2i_one64.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2i_launches_64GiB.csv python tools/one_scan.py 64 "because each" k=2 list=1 reps=2 > gpurun_out/r2i_ncu_launches.log 2>&1
+cat gpurun_out/r2i_one64.log
+grep -v "^==" gpurun_out/r2i_launches_64GiB.csv | tail -10 | awk -F'","' '{print substr($5,1,50), $NF}'
