@@ -29,6 +29,7 @@ __device__ __forceinline__ uint32_t windows_test(uint32_t lo, uint32_t hi, const
 			uint32_t r = (NA >= 2) ? __viaddmin_u32(w[t], P.coef[NA - 1], 0xFFFFFFFFu) : w[t] * P.one + P.coef[NA - 1];
 #pragma unroll
 			for (int i = NA - 2; i >= 0; i--) r = r * w[t] + P.coef[i];
+			if (MASKED) r *= P.scale;                            /* (two groups of three-byte anchors: both scaled) */
 			uint32_t q;
 			if (N3 == 1) q = w[t] * P.s256 + P.coef3[0];             /* 256 (w - B): coef3[0] = -256 B; s256: a run-time 256, so that this stays an IMAD (FMA pipe) and does not become a shift-add on the ALU pipe, which the min and funnel shifts already fill */
 			else {
@@ -193,6 +194,270 @@ static void launch_front_mixed(const FrontParams &P, bool fold, unsigned grid, c
 	if (P.n3 == 1) { if (fold) launch_front_one<NA, false, true, true, 1>(P, grid, st); else launch_front_one<NA, false, false, true, 1>(P, grid, st); }
 	else           { if (fold) launch_front_one<NA, false, true, true, 2>(P, grid, st); else launch_front_one<NA, false, false, true, 2>(P, grid, st); }
 }
+/* three-byte anchors whose one polynomial fails the false-positive guard (two of them share their first byte, "aus" and
+ * "ach"), split into two groups that pass it: both polynomials scaled by 256 */
+template <int NA>
+static void launch_front_split3(const FrontParams &P, bool fold, unsigned grid, cudaStream_t st)
+{
+	if (P.n3 == 1) { if (fold) launch_front_one<NA, true, true, true, 1>(P, grid, st); else launch_front_one<NA, true, false, true, 1>(P, grid, st); }
+	else           { if (fold) launch_front_one<NA, true, true, true, 2>(P, grid, st); else launch_front_one<NA, true, false, true, 2>(P, grid, st); }
+}
+
+/* ================================================================================================
+ * exact literal no longer than its anchor, count only (`agrep -c the`): no automaton at all.
+ *
+ * Every occurrence of the literal IS an anchor hit, so the number of matching records is the number of records that
+ * hold a hit: hits and delimiters are both properties of the bytes, and "the record of this hit already had one" is
+ * "no delimiter since the hit before".  One pass, the same persistent TMA ring as k_front; per 16-byte chunk the
+ * anchor test (one window per byte) and "is there a delimiter byte in here" (SWAR); the 32 chunks of a warp are stitched
+ * with ballots -- a hit starts a new record if a delimiter lies between it and the hit before -- and only chunks that
+ * hold both a hit and a delimiter look at byte positions.  A warp writes one summary word per 512 bytes where stage 1
+ * writes its bitmap word: records with a hit not counting the first hit's, and whether a delimiter lies before the
+ * first hit / after the last / anywhere; the summaries form a monoid under concatenation (k_exact_reduce).
+ * sgrep.c:731-795 (bm(): count the record, jump to its end), bitap.c:177-229 with a literal and no errors.
+ * ============================================================================================== */
+#define EX_HAS   (1u << 16)
+#define EX_LEAD  (1u << 17)
+#define EX_TRAIL (1u << 18)
+#define EX_ANY   (1u << 19)
+
+/* exact per-byte equality: 0x80 in every byte of x that equals the byte replicated in c4 */
+__device__ __forceinline__ uint32_t eq_bytes(uint32_t x, uint32_t c4)
+{
+	const uint32_t t = x ^ c4;
+	return ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t | 0x7F7F7F7Fu);
+}
+
+template <bool MASKED, bool FOLD, bool FULL>
+__device__ __forceinline__ void exact_chunks(const FrontParams &P, const uint8_t *st, uint32_t tid, uint32_t lane, uint32_t rem, uint32_t *bm, uint64_t stage_byte0)
+{
+	const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll 1
+	for (int c = 0; c < FRONT_CH; c++) {
+		const uint32_t idx = c * FRONT_THREADS + tid;
+		const uint4 v = *reinterpret_cast<const uint4 *>(st + idx * 16);
+		const uint32_t x4 = *reinterpret_cast<const uint32_t *>(st + idx * 16 + 16);
+		const uint32_t raw[5] = { v.x, v.y, v.z, v.w, x4 };
+		uint32_t x[5];
+#pragma unroll
+		for (int i = 0; i < 5; i++) x[i] = FOLD ? (raw[i] | P.fold) : raw[i];
+		/* any window == the anchor?  (one anchor: the unsigned minimum of the differences) */
+		uint32_t acc = 0xffffffffu;
+#pragma unroll
+		for (int w = 0; w < 4; w++) {
+			uint32_t wv[4] = { x[w], __funnelshift_r(x[w], x[w + 1], 8), __funnelshift_r(x[w], x[w + 1], 16), __funnelshift_r(x[w], x[w + 1], 24) };
+#pragma unroll
+			for (int j = 0; j < 4; j++) { const uint32_t dlt = (MASKED ? (wv[j] & P.amask) : wv[j]) - P.anchor[0]; wv[j] = dlt; }
+			acc = __vimin3_u32(acc, wv[0], wv[1]);
+			acc = __vimin3_u32(acc, wv[2], wv[3]);
+		}
+		bool hit = acc == 0;
+		/* a delimiter byte in the chunk? */
+		uint32_t z = 0;
+#pragma unroll
+		for (int w = 0; w < 4; w++) { const uint32_t t = raw[w] ^ P.delim4; z |= (t - 0x01010101u) & ~t; }
+		bool nl = (z & 0x80808080u) != 0;
+		uint32_t lead = 0, trail = 0, inner = 0;        /* of a chunk with a hit: delimiter before its first hit / after its last; hits that follow a delimiter inside it */
+		const int64_t base = (int64_t)stage_byte0 + (int64_t)idx * 16;
+		const bool tail = !FULL && (idx >= rem || base + 16 + 4 > (int64_t)P.n);
+		if (!FULL && idx >= rem) { hit = false; nl = false; }
+		uint32_t T = 0, L = 0, I = 0;                      /* ballots of trail / lead, sum of inner: only chunks that took the byte-position path have any */
+		if (__any_sync(0xffffffffu, (hit && nl) || (tail && (hit || nl)))) {
+			if ((hit && nl) || (tail && (hit || nl))) {
+				/* byte positions: hm = windows that equal the anchor, nm = delimiter bytes (both cut at the end of the text) */
+				uint32_t hm = 0, nm = 0;
+#pragma unroll
+				for (int w = 0; w < 4; w++) {
+					const uint32_t wv[4] = { x[w], __funnelshift_r(x[w], x[w + 1], 8), __funnelshift_r(x[w], x[w + 1], 16), __funnelshift_r(x[w], x[w + 1], 24) };
+#pragma unroll
+					for (int j = 0; j < 4; j++) if ((MASKED ? (wv[j] & P.amask) : wv[j]) == P.anchor[0]) hm |= 1u << (4 * w + j);
+					const uint32_t e = eq_bytes(raw[w], P.delim4);
+					nm |= ((((e >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * w);
+				}
+				if (tail) {
+					const int64_t nb = (int64_t)P.n - base;                 /* bytes of the text in this chunk */
+					const int64_t nh = nb - (int64_t)P.alen + 1;             /* windows that lie inside the text */
+					nm &= nb >= 16 ? 0xFFFFu : (nb <= 0 ? 0u : ((1u << nb) - 1u));
+					hm &= nh >= 16 ? 0xFFFFu : (nh <= 0 ? 0u : ((1u << nh) - 1u));
+					hit = hm != 0; nl = nm != 0;
+				}
+				if (hit) {
+					const int first = __ffs(hm) - 1, last = 31 - __clz(hm);
+					lead = (nm & ((1u << first) - 1u)) ? 1u : 0u;
+					trail = (nm >> last) > 1u ? 1u : 0u;                  /* a delimiter after the last hit's first byte (it cannot be inside the hit) */
+					for (uint32_t h = hm & (hm - 1); h; h &= h - 1) {       /* hits after the first: a delimiter since the hit before? */
+						const int cur = __ffs(h) - 1, prev = 31 - __clz(hm & ((1u << cur) - 1u));
+						inner += (nm & ((1u << cur) - 1u) & ~((2u << prev) - 1u)) ? 1u : 0u;
+					}
+				}
+			}
+			T = __ballot_sync(0xffffffffu, trail != 0);
+			L = __ballot_sync(0xffffffffu, lead != 0);
+			I = __reduce_add_sync(0xffffffffu, inner);
+		}
+		const uint32_t A = __ballot_sync(0xffffffffu, hit);
+		const uint32_t N = __ballot_sync(0xffffffffu, nl && !hit);          /* delimiters in chunks without a hit */
+		/* this hit starts a new record (within the warp's 512 bytes) if a delimiter lies between it and the hit before */
+		bool fresh = false;
+		if (hit && (A & lt)) {
+			const int j = 31 - __clz(A & lt);
+			fresh = lead || ((T >> j) & 1u) || (N & lt & ~((2u << j) - 1u));
+		}
+		const uint32_t F = __ballot_sync(0xffffffffu, fresh);
+		if (lane == 0 && (FULL || idx < rem)) {
+			uint32_t sum = __popc(F) + I;
+			if (A) {
+				const int fi = __ffs(A) - 1, la = 31 - __clz(A);
+				sum |= EX_HAS;
+				if (((L >> fi) & 1u) || (N & ((1u << fi) - 1u))) sum |= EX_LEAD;
+				if (((T >> la) & 1u) || (la < 31 && (N >> (la + 1)))) sum |= EX_TRAIL;
+			}
+			if (N || L || T || __popc(F) || I) sum |= EX_ANY;
+			bm[c * (FRONT_THREADS / 32)] = sum;
+		}
+	}
+}
+
+template <bool MASKED, bool FOLD>
+__global__ void __launch_bounds__(FRONT_THREADS, FRONT_CTAS_PER_SM)
+k_front_exact(const FrontParams P)
+{
+	extern __shared__ __align__(128) uint8_t s_ring[];
+	__shared__ uint64_t s_bar[FRONT_NST];
+	const uint32_t tid = threadIdx.x, lane = tid & 31;
+	if (tid == 0) {
+		for (int i = 0; i < FRONT_NST; i++) mbar_init(&s_bar[i], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	auto issue = [&](uint64_t it) {
+		const uint64_t sg = P.stage_begin + blockIdx.x + it * gridDim.x;
+		if (sg >= P.stage_end) return;
+		const uint32_t slot = (uint32_t)(it % FRONT_NST);
+		const uint64_t off = sg * FRONT_STAGE_BYTES, avail = P.readable - off;
+		const uint32_t bytes = (uint32_t)(avail < FRONT_SLOT_BYTES ? (avail & ~15ull) : FRONT_SLOT_BYTES);
+		mbar_expect_tx(&s_bar[slot], bytes);
+		bulk_g2s(s_ring + slot * FRONT_SLOT_BYTES, P.text + off, bytes, &s_bar[slot]);
+	};
+	if (tid == 0) for (int i = 0; i < FRONT_NST; i++) issue(i);
+	const uint32_t warp_in_cta = tid >> 5;
+	for (uint32_t it = 0;; it++) {
+		const uint64_t sg = P.stage_begin + blockIdx.x + (uint64_t)it * gridDim.x;
+		if (sg >= P.stage_end) break;
+		const uint32_t slot = it % FRONT_NST;
+		mbar_wait(&s_bar[slot], (it / FRONT_NST) & 1u);
+		const uint8_t *st = s_ring + slot * FRONT_SLOT_BYTES;
+		const uint64_t left = P.n_chunks - sg * FRONT_STAGE_CHUNKS;
+		const uint32_t rem = left > 0xFFFF0000ull ? 0xFFFF0000u : (uint32_t)left;
+		uint32_t *bm = P.bitmap + sg * FRONT_WORDS_PER_STAGE + warp_in_cta;
+		const bool full = left >= FRONT_STAGE_CHUNKS + 2;
+		if (full) exact_chunks<MASKED, FOLD, true>(P, st, tid, lane, rem, bm, sg * FRONT_STAGE_BYTES);
+		else exact_chunks<MASKED, FOLD, false>(P, st, tid, lane, rem, bm, sg * FRONT_STAGE_BYTES);
+		__syncthreads();
+		if (tid == 0) issue((uint64_t)it + FRONT_NST);
+	}
+}
+
+/* the summaries of consecutive 512-byte stretches, combined in order: {records with a hit beyond the first hit's, a hit at
+ * all, a delimiter before the first hit, after the last hit, anywhere} */
+struct ExSum { unsigned long long cnt; uint32_t fl; };
+__device__ __forceinline__ ExSum ex_combine(const ExSum a, const ExSum b)
+{
+	ExSum r;
+	if (!(b.fl & EX_HAS)) { r = a; if (b.fl & EX_ANY) r.fl |= EX_ANY | ((a.fl & EX_HAS) ? EX_TRAIL : 0u); return r; }
+	if (!(a.fl & EX_HAS)) { r = b; if (a.fl & EX_ANY) r.fl |= EX_ANY | EX_LEAD; return r; }
+	r.cnt = a.cnt + b.cnt + (((a.fl & EX_TRAIL) || (b.fl & EX_LEAD)) ? 1ull : 0ull);
+	r.fl = EX_HAS | (a.fl & EX_LEAD) | (b.fl & EX_TRAIL) | ((a.fl | b.fl) & EX_ANY);
+	return r;
+}
+#define EXR_THREADS 256
+#define EXR_PER     16
+/* level 0: block b combines summaries [b * 4096, (b + 1) * 4096) into part[b]; level 1 (final): one block combines part[] and
+ * writes the number of matching records */
+__global__ void __launch_bounds__(EXR_THREADS) k_exact_reduce(const uint32_t *sums, uint64_t n, ExSum *part_in, ExSum *part_out, unsigned long long *total)
+{
+	__shared__ ExSum s_w[EXR_THREADS / 32];
+	const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	ExSum acc; acc.cnt = 0; acc.fl = 0;
+	const uint64_t i0 = ((uint64_t)blockIdx.x * EXR_THREADS + tid) * EXR_PER;
+	for (int j = 0; j < EXR_PER; j++) {
+		const uint64_t i = i0 + j;
+		if (i >= n) break;
+		ExSum e;
+		if (part_in) e = part_in[i]; else { const uint32_t w = sums[i]; e.cnt = w & 0xFFFFu; e.fl = w & 0xFFFF0000u; }
+		acc = ex_combine(acc, e);
+	}
+	for (int o = 1; o < 32; o <<= 1) {
+		ExSum b; b.cnt = __shfl_down_sync(0xffffffffu, acc.cnt, o); b.fl = __shfl_down_sync(0xffffffffu, acc.fl, o);
+		if (lane + o < 32 && (lane % (2 * o)) == 0) acc = ex_combine(acc, b);
+	}
+	if (lane == 0) s_w[wid] = acc;
+	__syncthreads();
+	if (tid == 0) {
+		ExSum t = s_w[0];
+		for (int w = 1; w < EXR_THREADS / 32; w++) t = ex_combine(t, s_w[w]);
+		if (part_out) part_out[blockIdx.x] = t;
+		if (total) *total = t.cnt + ((t.fl & EX_HAS) ? 1ull : 0ull);
+	}
+}
+
+bool exact_count_usable(const agb_desc &d)
+{
+	if (!front_usable(d) || d.k != 0 || d.n_anchors != 1 || d.n_anchors3 || d.pat_len != d.anchor_len || d.inverse || d.L != 1 || d.and_mode) return false;
+	if (d.engine != AGB_ENGINE_BITAP && d.engine != AGB_ENGINE_SGREP_BM) return false;
+	if (d.wildmask || d.init1 == ~0ull) return false;
+	for (int t = 0; t < d.anchor_len; t++) {
+		const int c = (int)(d.anchor[0] >> (8 * t) & 0xFF);
+		if (c == d.delim[0]) return false;
+		/* the anchor test is exact for this byte: no fold, or a letter whose two cases are what the pattern accepts */
+		const uint64_t bit = 1ull << (d.M - (d.L + 2 + t));
+		int cnt = 0; for (int b = 0; b < 256; b++) if (d.mask[b] & bit) cnt++;
+		const bool alpha = (c | 32) >= 'a' && (c | 32) <= 'z';
+		if (d.anchor_fold) { if (!(alpha && cnt == 2 && (d.mask[c | 32] & bit) && (d.mask[(c | 32) - 32] & bit))) return false; }
+		else if (!(cnt == 1 && (d.mask[c] & bit))) return false;
+	}
+	return true;
+}
+
+/* count of the records that hold the literal: the exact pass + the ordered reduction of its summaries into totals[0] */
+int exact_count_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, cudaStream_t st)
+{
+	const uint64_t n_chunks = (n + 15) / 16, n_words = (n_chunks + 31) / 32;
+	if (!n_words) return AGB_OK;
+	FrontParams F; memset(&F, 0, sizeof F);
+	F.text = (const uint8_t *)d_text; F.bitmap = W.bitmap; F.n = n; F.n_chunks = n_chunks;
+	F.readable = n_chunks * 16;
+	F.stage_begin = 0; F.stage_end = (n_words + FRONT_WORDS_PER_STAGE - 1) / FRONT_WORDS_PER_STAGE;
+	F.fold = d.anchor_fold; F.amask = d.anchor_mask; F.anchor[0] = d.anchor[0]; F.alen = d.anchor_len;
+	F.delim4 = d.delim[0] * 0x01010101u;
+	const unsigned grid = (unsigned)std::min<uint64_t>(F.stage_end, (uint64_t)W.sm_count * FRONT_CTAS_PER_SM);
+	const bool masked = d.anchor_mask != 0xFFFFFFFFu, fold = d.anchor_fold != 0;
+	static bool configured[64][4] = {{false}};
+	int dev = 0; cudaGetDevice(&dev);
+#define EX_LAUNCH(M_, F_) do { if (!configured[dev & 63][(M_) * 2 + (F_)]) { cudaFuncSetAttribute(k_front_exact<M_, F_>, cudaFuncAttributeMaxDynamicSharedMemorySize, FRONT_SMEM); configured[dev & 63][(M_) * 2 + (F_)] = true; } \
+	k_front_exact<M_, F_><<<grid, FRONT_THREADS, FRONT_SMEM, st>>>(F); } while (0)
+	if (masked) { if (fold) EX_LAUNCH(true, true); else EX_LAUNCH(true, false); }
+	else { if (fold) EX_LAUNCH(false, true); else EX_LAUNCH(false, false); }
+#undef EX_LAUNCH
+	g_launches++;
+	CUDA_TRY(cudaGetLastError());
+	/* ordered reduction: 4096 summaries per block, then one block over the block results (W.tile_offsets as scratch: 16 B each) */
+	const uint64_t per_block = (uint64_t)EXR_THREADS * EXR_PER, nb = (n_words + per_block - 1) / per_block;
+	if ((nb + nb / per_block + 16) * sizeof(ExSum) > W.tiles * sizeof(uint64_t)) { snprintf(g_err, sizeof g_err, "internal: scratch too small for the exact count"); return AGB_ERR_NOMEM; }
+	ExSum *part = reinterpret_cast<ExSum *>(W.tile_offsets);
+	if (nb == 1) { k_exact_reduce<<<1, EXR_THREADS, 0, st>>>(W.bitmap, n_words, nullptr, nullptr, W.totals); g_launches++; }
+	else {
+		k_exact_reduce<<<(unsigned)nb, EXR_THREADS, 0, st>>>(W.bitmap, n_words, nullptr, part, nullptr); g_launches++;
+		uint64_t m = nb; ExSum *in = part, *outp = part + nb;
+		while (m > 1) {
+			const uint64_t mb = (m + per_block - 1) / per_block;
+			k_exact_reduce<<<(unsigned)mb, EXR_THREADS, 0, st>>>(nullptr, m, in, mb == 1 ? nullptr : outp, mb == 1 ? W.totals : nullptr); g_launches++;
+			in = outp; outp += mb; m = mb;
+		}
+	}
+	CUDA_TRY(cudaGetLastError());
+	return AGB_OK;
+}
 
 /* coefficients of prod_i (x - a_i) mod 2^32 and the false-positive guard of the polynomial form:
  * a zero product without a zero factor needs sum_i v2(w - a_i) >= bits; with t = the largest v2(a_i - a_j)
@@ -273,6 +538,31 @@ int front_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n
 		g_launches++;
 		CUDA_TRY(cudaGetLastError());
 		return AGB_OK;
+	}
+	if (!poly && d.anchor_len == 3 && na >= 2 && na <= 5) {
+		/* split: anchors into group A while its guard holds, the rest (at most two) into group B */
+		uint32_t ga[AGB_MAXANCHOR], gb[4], ca[AGB_MAXANCHOR], cb[AGB_MAXANCHOR]; int nga = 0, ngb = 0; bool ok = true;
+		for (int i = 0; i < na && ok; i++) {
+			ga[nga] = F.anchor[i];
+			if (poly_setup(ga, nga + 1, 24, ca)) { nga++; continue; }
+			if (ngb >= 2) { ok = false; break; }
+			gb[ngb] = F.anchor[i];
+			if (!poly_setup(gb, ngb + 1, 24, cb)) ok = false; else ngb++;
+		}
+		if (ok && ngb >= 1 && nga >= 1) {
+			poly_setup(ga, nga, 24, ca); poly_setup(gb, ngb, 24, cb);
+			for (int i = 0; i < nga; i++) F.coef[i] = ca[i];
+			F.n3 = ngb;
+			for (int i = 0; i < ngb; i++) F.coef3[i] = cb[i];
+			if (ngb == 1) F.coef3[0] = 0u - 256u * gb[0];
+			switch (nga) {
+			case 1: launch_front_split3<1>(F, fold, grid, st); break;  case 2: launch_front_split3<2>(F, fold, grid, st); break;
+			case 3: launch_front_split3<3>(F, fold, grid, st); break;  default: launch_front_split3<4>(F, fold, grid, st); break;
+			}
+			g_launches++;
+			CUDA_TRY(cudaGetLastError());
+			return AGB_OK;
+		}
 	}
 #define FRONT_CASE(N) case N: if (poly) launch_front_na<N, true>(F, masked, fold, grid, st); else launch_front_na<N, false>(F, masked, fold, grid, st); break;
 	switch (na) {

@@ -400,6 +400,19 @@ int scan_device_impl(const agb_desc &d_in, const void *d_text, uint64_t n, int w
 	agb_desc planned;
 	rc = adaptive_plan(d_in, W, d_text, n, st, &planned); if (rc) return rc;
 	const agb_desc &d = planned;
+	if (want == AGB_WANT_COUNT && !sh && n >= (1u << 20) && exact_count_usable(d)) {
+		/* `agrep -c the`: an exact literal no longer than its anchor needs no automaton (front.cu, exact_count_launch) */
+		CUDA_TRY(cudaMemsetAsync(W.totals, 0, 16 * sizeof(unsigned long long), st));
+		CUDA_TRY(cudaEventRecord(W.e0, st));
+		rc = exact_count_launch(d, W, d_text, n, st); if (rc) return rc;
+		CUDA_TRY(cudaEventRecord(W.e1, st));
+		CUDA_TRY(cudaEventRecord(W.e2, st));
+		rc = fetch_result(W, want, capacity, false, st, res); if (rc) return rc;
+		res->n_flagged = 0;
+		CUDA_TRY(cudaEventElapsedTime(&res->ms_front, W.e0, W.e1));
+		res->ms_records = 0;
+		return AGB_OK;
+	}
 	rc = ws_upload_desc(W, d, st); if (rc) return rc;
 	CUDA_TRY(cudaMemsetAsync(W.totals, 0, 16 * sizeof(unsigned long long), st));
 	CUDA_TRY(cudaEventRecord(W.e0, st));

@@ -49,6 +49,7 @@ struct FrontParams {
 	uint32_t     coef[AGB_MAXANCHOR];   /* prod_i (x - anchor[i]) mod 2^32, low order first, leading 1 implied */
 	int          n3;             /* mixed plan: three-byte anchors, their polynomial (scaled by 256 in the kernel) */
 	uint32_t     s256;
+	int          alen;           /* exact count: bytes of the literal */
 	uint32_t     coef3[4];
 	uint16_t    *nl_blocks;      /* COUNT: delimiter bytes per 512-byte block = per bitmap word (the ordinals' first pass, fused) */
 	uint32_t     delim4;         /* the 1-byte delimiter, four times */
@@ -177,6 +178,8 @@ int  scan_device_impl(const agb_desc &d, const void *d_text, uint64_t n, int wan
                       agb_record *d_records, uint64_t capacity, cudaStream_t st, agb_result *res, const ShardInfo *sh = nullptr);
 /* front.cu */
 bool front_usable(const agb_desc &d);
+bool exact_count_usable(const agb_desc &d);
+int  exact_count_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, cudaStream_t st);
 bool poly_setup(const uint32_t *a, int na, int bits, uint32_t *coef);
 int  front_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, uint64_t word_begin, uint64_t word_end, bool slack16, cudaStream_t st, bool count_delims = false);
 /* refine.cu */

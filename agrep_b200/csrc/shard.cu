@@ -15,6 +15,48 @@
  */
 #include "scan_internal.cuh"
 #include <nccl.h>
+#include <dlfcn.h>
+
+/* NCCL is bound at run time, not at link time: a process that also runs PyTorch must end up with ONE libnccl.so.2, and
+ * PyTorch brings its own (newer) one -- had this library the system's as a link-time dependency, importing it first would
+ * pin that older one under the same soname and libtorch_cuda.so would fail to resolve its symbols.  dlopen() by soname
+ * returns whatever copy is already loaded, else the system's. */
+static struct NcclApi {
+	void *h;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+	ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+	ncclResult_t (*CommDestroy)(ncclComm_t);
+	ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+	ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+	ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+	ncclResult_t (*GroupStart)(void);
+	ncclResult_t (*GroupEnd)(void);
+	const char *(*GetErrorString)(ncclResult_t);
+} g_nccl;
+
+static int nccl_load(void)
+{
+	if (g_nccl.h) return AGB_OK;
+	void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+	if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+	if (!h) { snprintf(g_err, sizeof g_err, "NCCL is not available: %s", dlerror()); return AGB_ERR_CUDA; }
+#define NCCL_SYM(field, name) do { *(void **)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) { snprintf(g_err, sizeof g_err, "libnccl lacks %s", name); return AGB_ERR_CUDA; } } while (0)
+	NCCL_SYM(GetUniqueId, "ncclGetUniqueId"); NCCL_SYM(CommInitRank, "ncclCommInitRank"); NCCL_SYM(CommDestroy, "ncclCommDestroy");
+	NCCL_SYM(AllGather, "ncclAllGather"); NCCL_SYM(Send, "ncclSend"); NCCL_SYM(Recv, "ncclRecv");
+	NCCL_SYM(GroupStart, "ncclGroupStart"); NCCL_SYM(GroupEnd, "ncclGroupEnd"); NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef NCCL_SYM
+	g_nccl.h = h;
+	return AGB_OK;
+}
+#define ncclGetUniqueId    g_nccl.GetUniqueId
+#define ncclCommInitRank   g_nccl.CommInitRank
+#define ncclCommDestroy    g_nccl.CommDestroy
+#define ncclAllGather      g_nccl.AllGather
+#define ncclSend           g_nccl.Send
+#define ncclRecv           g_nccl.Recv
+#define ncclGroupStart     g_nccl.GroupStart
+#define ncclGroupEnd       g_nccl.GroupEnd
+#define ncclGetErrorString g_nccl.GetErrorString
 
 #define NCCL_TRY(x) do { ncclResult_t r_ = (x); if (r_ != ncclSuccess) { \
 	snprintf(g_err, sizeof g_err, "%s failed: %s (%s:%d)", #x, ncclGetErrorString(r_), __FILE__, __LINE__); \
@@ -39,6 +81,7 @@ extern "C" int agb_comm_unique_id(void *id128)
 {
 	ncclUniqueId id;
 	if (!id128) return AGB_ERR_ARG;
+	{ int rc = nccl_load(); if (rc) return rc; }
 	NCCL_TRY(ncclGetUniqueId(&id));
 	static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
 	memcpy(id128, &id, sizeof id);
@@ -48,6 +91,7 @@ extern "C" int agb_comm_unique_id(void *id128)
 extern "C" int agb_comm_init(agb_comm **out, int world, int rank, const void *id128)
 {
 	if (!out || !id128 || world < 1 || world > SHARD_MAXWORLD || rank < 0 || rank >= world) return AGB_ERR_ARG;
+	{ int rc = nccl_load(); if (rc) return rc; }
 	agb_comm *c = new agb_comm; memset(c, 0, sizeof *c);
 	c->world = world; c->rank = rank;
 	CUDA_TRY(cudaGetDevice(&c->dev));

@@ -318,3 +318,28 @@ def test_host_entry_points_agree(tmp_path):
     a = _oracle.compile("because each", k=2, linenum=1)
     cnt, orecs = _oracle.scan(a, small)
     assert res.n_matched == cnt and [(recs[i].begin, recs[i].end) for i in range(res.n_records)] == [(b, e) for b, e, _ in orecs]
+
+
+def test_exact_literal_count_path():
+    """`agrep -c the`: an exact literal no longer than its anchor, count only, texts of 1 MiB and more -> the pass that
+    needs no automaton (k_front_exact + k_exact_reduce: records that hold a hit, stitched from chunk, warp and block
+    summaries).  Against the oracle, and against the same library's list path; ragged ends: no final newline, the text
+    ending inside an occurrence, an occurrence at the very end."""
+    body = _corpus.make_text(60000, seed=77)
+    assert len(body) > (2 << 20)
+    cases = [("the", {}), ("The", {}), ("and", {}), ("that", {}), ("of", {}), ("the", dict(linenum=1)), ("the", dict(linenum=1, nocase=1)),
+             ("state", {}), ("e", dict(linenum=1)), ("the", dict(delim=";")), ("zqx", {})]
+    texts = [body, body[:-1], body + b"xx th", body + b"the", body.replace(b"\n", b";", 20000), b"the" * 400000, body.replace(b" ", b"\n")]
+    for data in texts:
+        for pat, kw in cases:
+            try:
+                a = _oracle.compile(pat, **kw)
+            except _oracle.OracleError:
+                continue
+            cnt, _ = _oracle.scan(a, data, want_records=False)
+            p = ag.Pattern(pat, **api_kw(kw))
+            got = p.scan_host(data, want_records=False)[0].n_matched          # host entry (streamed: the automaton forms)
+            import torch
+            t = torch.frombuffer(bytearray(data + b"\0" * 64), dtype=torch.uint8).cuda()
+            dev = p.scan_device(t.data_ptr(), len(data)).n_matched             # device entry, count only: the exact pass when it applies
+            assert got == cnt and dev == cnt, (pat, kw, len(data), got, dev, cnt)

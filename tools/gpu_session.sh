@@ -1,6 +1,6 @@
 set -x
 cd $GRAFT_REPO_ROOT
-AGB_DEBUG_PLAN=1 timeout 300 python tools/one_scan.py 64 "because each" k=2 list=1 reps=4 > gpurun_out/r2i_one64.log 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2i_launches_64GiB.csv python tools/one_scan.py 64 "because each" k=2 list=1 reps=2 > gpurun_out/r2i_ncu_launches.log 2>&1
-cat gpurun_out/r2i_one64.log
-grep -v "^==" gpurun_out/r2i_launches_64GiB.csv | tail -10 | awk -F'","' '{print substr($5,1,50), $NF}'
+timeout 1800 python -m pytest tests -x -q -m gpu 2>&1 | tail -25 > gpurun_out/r2k_tests.log
+tail -8 gpurun_out/r2k_tests.log
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_front_exact -s 1 -c 1 -f -o /tmp/r2k_exact python tools/one_scan.py 8 "the" > gpurun_out/r2k_ncu_exact.log 2>&1
+tools/ncu_export.sh /tmp/r2k_exact.ncu-rep gpurun_out/r2k_exact
