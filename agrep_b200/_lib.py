@@ -33,7 +33,8 @@ class Desc(C.Structure):
                 ("plan", C.c_int32), ("n_anchors", C.c_int32), ("anchor_len", C.c_int32),
                 ("anchor", C.c_uint32 * AGB_MAXANCHOR), ("anchor_fold", C.c_uint32), ("anchor_mask", C.c_uint32),
                 ("refine", C.c_int32), ("pat_len", C.c_int32), ("anchor_off", C.c_int32 * AGB_MAXANCHOR),
-                ("n_anchors3", C.c_int32), ("anchor3", C.c_uint32 * 4), ("anchor3_off", C.c_int32 * 4), ("adaptive", C.c_int32)]
+                ("n_anchors3", C.c_int32), ("anchor3", C.c_uint32 * 4), ("anchor3_off", C.c_int32 * 4), ("adaptive", C.c_int32),
+                ("delim_fold", C.c_uint8 * (2 * AGB_MAXDELIM + 2)), ("pad_", C.c_uint8 * 2)]
 
 
 class Record(C.Structure):

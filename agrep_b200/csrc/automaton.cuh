@@ -30,7 +30,8 @@ template <typename T> struct DevConsts {
 template <typename T, int NR> struct RecShared {
 	T mask[257];                 /* mask[256] = 0: "a byte outside the text" */
 	T reset[NR], start[NR];
-	uint8_t delim[2 * AGB_MAXDELIM + 2];
+	uint8_t delim[2 * AGB_MAXDELIM + 2];     /* lower case where both cases end a record (dfold) */
+	uint8_t dfold[2 * AGB_MAXDELIM + 2];
 	unsigned long long hist[AGB_MAXERR + 1];
 	int start_closes;
 };
@@ -41,7 +42,7 @@ __device__ __forceinline__ void shared_init(RecShared<T, NR> &S, DevConsts<T> &C
 	for (int i = threadIdx.x; i < 256; i += nthreads) S.mask[i] = mirror<T>((T)D->mask[i]);
 	if (threadIdx.x == 0) { S.mask[256] = 0; S.start_closes = D->start_closes; }
 	if (threadIdx.x < NR) { S.reset[threadIdx.x] = mirror<T>((T)D->reset[threadIdx.x]); S.start[threadIdx.x] = mirror<T>((T)D->start[threadIdx.x]); }
-	if (threadIdx.x < 2 * AGB_MAXDELIM + 2) S.delim[threadIdx.x] = D->delim[threadIdx.x];
+	if (threadIdx.x < 2 * AGB_MAXDELIM + 2) { S.dfold[threadIdx.x] = D->delim_fold[threadIdx.x]; S.delim[threadIdx.x] = D->delim[threadIdx.x] | D->delim_fold[threadIdx.x]; }
 	if (threadIdx.x <= AGB_MAXERR) S.hist[threadIdx.x] = 0;
 	C.init1 = mirror<T>((T)D->init1); C.noerr = mirror<T>((T)D->noerr); C.endpos = mirror<T>((T)D->endpos); C.dendpos = mirror<T>((T)D->dendpos);
 	C.L = D->L; C.k = D->k; C.and_mode = D->and_mode; C.inverse = D->inverse; C.kind = D->delim_kind;
@@ -84,17 +85,17 @@ struct WindowReader {
  * does (no self overlap); kind 1 (c^L, e.g. $$): greedy, non-overlapping from the start of the run of c,
  * the virtual '\n' counting as part of the run (asearch.c:55-57 D_Mask + the reset at :181). */
 template <typename RD>
-__device__ __forceinline__ bool delim_ends_at(RD &R, int64_t q, const uint8_t *delim, int L, int kind)
+__device__ __forceinline__ bool delim_ends_at(RD &R, int64_t q, const uint8_t *delim, const uint8_t *dfold, int L, int kind)
 {
-	if (L == 1) return R.get(q) == delim[0];
+	if (L == 1) return (R.get(q) | dfold[0]) == delim[0];
 	if (kind == 0) {
-		for (int t = 0; t < L; t++) if (R.get(q - t) != delim[L - 1 - t]) return false;
+		for (int t = 0; t < L; t++) if ((R.get(q - t) | dfold[L - 1 - t]) != delim[L - 1 - t]) return false;
 		return true;
 	}
-	int c = delim[0];
-	if (R.get(q) != c) return false;
+	const int c = delim[0], f = dfold[0];
+	if ((R.get(q) | f) != c) return false;
 	int64_t len = 1, p = q - 1;
-	while (p >= -1 && R.get(p) == c) { len++; p--; }
+	while (p >= -1 && (R.get(p) | f) == c) { len++; p--; }
 	return (len % L) == 0;
 }
 

@@ -257,20 +257,20 @@ extern "C" int agb_corpus_fill_host(const agb_corpus_spec *s, void *h_text)
 __device__ __forceinline__ uint32_t ord_count_seq(Reader &R, const OrdParams &P, int64_t from, int64_t to)
 {
 	uint32_t cnt = 0;
-	if (P.L == 1) { for (int64_t q = from; q < to; q++) cnt += R.get(q) == P.delim[0]; return cnt; }
+	if (P.L == 1) { for (int64_t q = from; q < to; q++) cnt += (R.get(q) | P.dfold[0]) == P.delim[0]; return cnt; }
 	if (P.kind == 0) {
 		for (int64_t q = from; q < to; q++) {
 			bool m = true;
-			for (int u = 0; u < P.L && m; u++) m = R.get(q - u) == P.delim[P.L - 1 - u];
+			for (int u = 0; u < P.L && m; u++) m = (R.get(q - u) | P.dfold[P.L - 1 - u]) == P.delim[P.L - 1 - u];
 			cnt += m ? 1u : 0u;
 		}
 		return cnt;
 	}
-	const int c = P.delim[0];
+	const int c = P.delim[0], f = P.dfold[0];
 	int64_t run = 0;
-	for (int64_t q = from - 1; q >= -1 && R.get(q) == c; q--) run++;       /* (-1 is the virtual '\n') */
+	for (int64_t q = from - 1; q >= -1 && (R.get(q) | f) == c; q--) run++;       /* (-1 is the virtual '\n') */
 	for (int64_t q = from; q < to; q++) {
-		run = R.get(q) == c ? run + 1 : 0;
+		run = (R.get(q) | f) == c ? run + 1 : 0;
 		cnt += (run > 0 && run % P.L == 0) ? 1u : 0u;
 	}
 	return cnt;
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(ORD_THREADS) k_delim_count(const OrdParams P)
 	if (P.L == 1 && tile0 + ORD_TILE <= n) {
 		/* a warp takes a 512-byte block per iteration, 16 bytes per lane (coalesced): exact per-byte equality by
 		 * SWAR (0x80 where the byte equals the delimiter), one warp reduction per block */
-		const uint32_t d4 = P.delim[0] * 0x01010101u;
+		const uint32_t d4 = P.delim[0] * 0x01010101u, f4 = P.dfold[0] * 0x01010101u;
 #pragma unroll
 		for (int it = 0; it < ORD_TILE / ORD_BLOCK / (ORD_THREADS / 32); it++) {
 			const uint32_t blk = wid * (ORD_TILE / ORD_BLOCK / (ORD_THREADS / 32)) + it;
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(ORD_THREADS) k_delim_count(const OrdParams P)
 			uint32_t c = 0;
 #pragma unroll
 			for (int w = 0; w < 4; w++) {
-				const uint32_t t = xs[w] ^ d4;
+				const uint32_t t = (xs[w] | f4) ^ d4;
 				c += __popc(~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t | 0x7F7F7F7Fu));
 			}
 			const uint32_t b = __reduce_add_sync(0xffffffffu, c);
@@ -398,10 +398,11 @@ int ordinals_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_
 	OrdParams P; memset(&P, 0, sizeof P);
 	P.text = (const uint8_t *)d_text; P.n = n; P.blocks = W.ord_blocks; P.tiles = W.tile_counts; P.tile_off = W.tile_offsets;
 	P.records = d_records; P.totals = W.totals; P.capacity = capacity;
-	memcpy(P.delim, d.delim, AGB_MAXDELIM + 2 < sizeof d.delim ? AGB_MAXDELIM + 2 : sizeof d.delim);
+	for (int i = 0; i < AGB_MAXDELIM + 2; i++) { P.dfold[i] = d.delim_fold[i]; P.delim[i] = d.delim[i] | d.delim_fold[i]; }
 	P.L = d.L; P.kind = d.delim_kind;
 	W.ord_virt = (d.L == 1 && d.delim[0] == '\n') ? 1 : 0;
 	/* bitap.c:151-156: j starts at -1 when the text begins with the user's delimiter (asearch0() has no such correction) */
+	/* (this one check is byte for byte against the delimiter as typed, also under -i: bitap.c:151-154 compares old_D_pat) */
 	P.j0 = (d.user_delim && d.engine != AGB_ENGINE_ASEARCH0 && n >= (uint64_t)d.L && memcmp(h_head, d.delim, (size_t)d.L) == 0) ? -1 : 0;
 	W.ord_j0 = P.j0;
 	if (blocks_counted) { k_ord_tiles<<<(unsigned)((tiles + 255) / 256), 256, 0, st>>>(P, tiles); g_launches++; }     /* stage 1 counted the blocks */

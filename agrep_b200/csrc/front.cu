@@ -86,7 +86,7 @@ __device__ __forceinline__ void front_chunks(const FrontParams &P, const uint8_t
 			uint32_t cn = 0;
 #pragma unroll
 			for (int w = 0; w < 4; w++) {
-				const uint32_t t = xs[w] ^ P.delim4;
+				const uint32_t t = (xs[w] | P.dfold4) ^ P.delim4;
 				uint32_t z = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t | 0x7F7F7F7Fu);
 				if (!FULL) {                                     /* only bytes of the text */
 					/* rem chunks are left from the start of the stage, the last one padded: bytes of this word inside the text */
@@ -405,7 +405,7 @@ bool exact_count_usable(const agb_desc &d)
 {
 	if (!front_usable(d) || d.k != 0 || d.n_anchors != 1 || d.n_anchors3 || d.pat_len != d.anchor_len || d.inverse || d.L != 1 || d.and_mode) return false;
 	if (d.engine != AGB_ENGINE_BITAP && d.engine != AGB_ENGINE_SGREP_BM) return false;
-	if (d.wildmask || d.init1 == ~0ull) return false;
+	if (d.wildmask || d.init1 == ~0ull || d.delim_fold[0]) return false;
 	for (int t = 0; t < d.anchor_len; t++) {
 		const int c = (int)(d.anchor[0] >> (8 * t) & 0xFF);
 		if (c == d.delim[0]) return false;
@@ -497,7 +497,7 @@ int front_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n
 	F.stage_begin = word_begin / FRONT_WORDS_PER_STAGE;
 	F.stage_end = (word_end + FRONT_WORDS_PER_STAGE - 1) / FRONT_WORDS_PER_STAGE;
 	F.fold = d.anchor_fold; F.amask = d.anchor_mask;
-	F.nl_blocks = count_delims ? W.ord_blocks : nullptr; F.delim4 = d.delim[0] * 0x01010101u;
+	F.nl_blocks = count_delims ? W.ord_blocks : nullptr; F.dfold4 = d.delim_fold[0] * 0x01010101u; F.delim4 = (d.delim[0] | d.delim_fold[0]) * 0x01010101u;
 	const uint64_t stages = F.stage_end - F.stage_begin;
 	unsigned grid = (unsigned)std::min<uint64_t>(stages, (uint64_t)W.sm_count * FRONT_CTAS_PER_SM);
 	if (!grid) grid = 1;

@@ -242,6 +242,8 @@ static int has_border(const unsigned char *d, int L)
 	for (b = 1; b < L; b++) if (memcmp(d, d + L - b, (size_t)b) == 0) return 1;
 	return 0;
 }
+/* the delimiter as the device compares it: letters that accept both cases in lower case */
+static void folded_delim(const agb_desc *d, unsigned char *out) { int p; for (p = 0; p < d->L; p++) out[p] = (unsigned char)(d->delim[p] | d->delim_fold[p]); }
 
 /* derive the words from the positions (maskgen.c:218-257 with WORD = 64, LSB aligned) and the device-only constants */
 static int finish(build_t *b, agb_desc *d, const agb_options *o, const unsigned char *lut, char *err, size_t errlen)
@@ -305,16 +307,21 @@ int agbi_derive(agb_desc *d, char *err, size_t errlen)
 	 * bytes "a ... b" then closes a record like "ab" does.  One byte is fine (its only position is D_endpos itself). */
 	if (d->init1 == ~0ull && L > 1)
 		FAIL("-p with a delimiter of more than one byte is not supported (insertions inside the delimiter would be free too)");
+	memset(d->delim_fold, 0, sizeof d->delim_fold);
 	for (p = 1; p <= L; p++) {
-		const uint64_t bit = 1ull << (d->M - p); int c;
-		for (c = 0; c < 256; c++)
-			if (((d->mask[c] & bit) != 0) != (c == d->delim[p - 1]))
-				FAIL("the delimiter matches more than its own bytes here (-i with letters in the delimiter): not supported by the device record search");
+		const uint64_t bit = 1ull << (d->M - p); int c, cnt = 0, lo = d->delim[p - 1] | 0x20;
+		for (c = 0; c < 256; c++) if (d->mask[c] & bit) cnt++;
+		if (cnt == 1 && (d->mask[d->delim[p - 1]] & bit)) continue;
+		/* -i with a letter in the delimiter: both cases end the record (maskgen.c:52-58, 259-266) */
+		if (cnt == 2 && lo >= 'a' && lo <= 'z' && (d->mask[lo] & bit) && (d->mask[lo - 32] & bit)) { d->delim_fold[p - 1] = 0x20; continue; }
+		FAIL("the delimiter matches more than its own bytes here: not supported by the device record search");
 	}
 	/* delimiter recognition away from the automaton (record-start search on the device) */
-	if (L == 1 || !has_border(d->delim, L)) d->delim_kind = 0;
+	unsigned char fd[2 * AGB_MAXDELIM + 2];
+	folded_delim(d, fd);
+	if (L == 1 || !has_border(fd, L)) d->delim_kind = 0;
 	else {
-		for (p = 1; p < L; p++) if (d->delim[p] != d->delim[0]) break;
+		for (p = 1; p < L; p++) if (fd[p] != fd[0]) break;
 		if (p < L) FAIL("delimiter '%.*s' overlaps itself in a way the device record search does not support "
 		                "(supported: any 1-byte delimiter, self-overlap-free delimiters, and runs such as $$)", L, d->delim);
 		d->delim_kind = 1;
@@ -555,19 +562,23 @@ const agb_desc *agb_pattern_desc(const agb_pattern *p) { return p ? &p->d : NULL
 void agb_fill_ordinals(const agb_pattern *p, const void *h_text, uint64_t n, agb_record *records, uint64_t n_records)
 {
 	const agb_desc *d = &p->d; const unsigned char *t = (const unsigned char *)h_text;
-	const int L = d->L; uint64_t i = 0; long long j = 0, run = 0, q;
+	const int L = d->L; uint64_t i = 0; long long j = 0, run = 0, q; unsigned char fd[2 * AGB_MAXDELIM + 2]; int z, head = 1;
 	if (!n_records) return;
+	folded_delim(d, fd);
+#define DEQ(c, p) ((((c) | d->delim_fold[p]) & 0x1FF) == fd[p])
+	(void)z; (void)head;
+	/* (byte for byte against the delimiter as typed, also under -i: bitap.c:151-154 compares old_D_pat) */
 	if (d->user_delim && d->engine != AGB_ENGINE_ASEARCH0 && n >= (uint64_t)L && memcmp(t, d->delim, (size_t)L) == 0) j = -1;
 	/* position q = -1 is the virtual '\n'; positions n .. n+L-1 are the delimiter appended at EOF */
 	for (q = -1; q < (long long)n + L && i < n_records; q++) {
 		int c = q < 0 ? '\n' : (q < (long long)n ? t[q] : d->delim[q - (long long)n]), e;
-		if (L == 1) e = c == d->delim[0];
-		else if (d->delim_kind == 1) { run = c == d->delim[0] ? run + 1 : 0; e = run > 0 && run % L == 0; }
+		if (L == 1) e = DEQ(c, 0);
+		else if (d->delim_kind == 1) { run = DEQ(c, 0) ? run + 1 : 0; e = run > 0 && run % L == 0; }
 		else {
 			int m = 1, u;
 			for (u = 0; u < L && m; u++) {
 				long long at = q - u; int cc = at < -1 ? 256 : (at < 0 ? '\n' : (at < (long long)n ? t[at] : d->delim[at - (long long)n]));
-				if (cc != d->delim[L - 1 - u]) m = 0;
+				if (!DEQ(cc, L - 1 - u)) m = 0;
 			}
 			e = m;
 		}

@@ -34,11 +34,11 @@ __device__ __forceinline__ uint32_t chunk_records(const RecParams &P, const DevC
 			if (prev_flagged != -2) { if (cc == prev_flagged) break; }
 			else { const uint32_t pw = P.bitmap ? P.bitmap[cc >> 5] : 0xffffffffu; if (pw >> (cc & 31) & 1u) break; }
 			for (int64_t q = cc * 16 + 15; q >= cc * 16; q--)
-				if (delim_ends_at(R, q, SH.delim, L, C.kind)) { s = q + 1; found = true; break; }
+				if (delim_ends_at(R, q, SH.delim, SH.dfold, L, C.kind)) { s = q + 1; found = true; break; }
 		}
 		if (!found) {
 			for (int64_t q = lo; q <= hi && q < n; q++)
-				if (delim_ends_at(R, q, SH.delim, L, C.kind)) { s = q + 1; break; }
+				if (delim_ends_at(R, q, SH.delim, SH.dfold, L, C.kind)) { s = q + 1; break; }
 		}
 	}
 	/* run records while their re-fed byte (s-1) is at or before the end of this chunk */
@@ -186,7 +186,7 @@ k_records_dense(const RecParams P)
 	for (int w = 0; w < DENSE_PER / 64; w++) bits[w] = 0;
 	if (L == 1) {
 		/* 16 bytes at a time: exact per-byte equality by SWAR, 4 flags gathered by one multiply */
-		const uint32_t d4 = SH.delim[0] * 0x01010101u;
+		const uint32_t d4 = SH.delim[0] * 0x01010101u, f4 = SH.dfold[0] * 0x01010101u;
 #pragma unroll
 		for (int v = 0; v < DENSE_PER / 16; v++) {
 			const uint4 x = *reinterpret_cast<const uint4 *>(s_text + tid * DENSE_PER + v * 16);
@@ -194,7 +194,7 @@ k_records_dense(const RecParams P)
 			uint32_t m16 = 0;
 #pragma unroll
 			for (int w = 0; w < 4; w++) {
-				const uint32_t t = xs[w] ^ d4;
+				const uint32_t t = (xs[w] | f4) ^ d4;
 				const uint32_t z = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t | 0x7F7F7F7Fu);    /* 0x80 where the byte equals the delimiter */
 				m16 |= ((((z >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * w);
 			}
@@ -203,7 +203,7 @@ k_records_dense(const RecParams P)
 	} else {
 		for (uint32_t j = 0; j < DENSE_PER; j++) {
 			const int64_t q = tile0 + (int64_t)tid * DENSE_PER + j;
-			if (q < n && delim_ends_at(R, q, SH.delim, L, C.kind)) bits[j >> 6] |= 1ull << (j & 63);
+			if (q < n && delim_ends_at(R, q, SH.delim, SH.dfold, L, C.kind)) bits[j >> 6] |= 1ull << (j & 63);
 		}
 	}
 	{   /* only delimiters inside the text (q < n) */

@@ -52,7 +52,7 @@ struct FrontParams {
 	int          alen;           /* exact count: bytes of the literal */
 	uint32_t     coef3[4];
 	uint16_t    *nl_blocks;      /* COUNT: delimiter bytes per 512-byte block = per bitmap word (the ordinals' first pass, fused) */
-	uint32_t     delim4;         /* the 1-byte delimiter, four times */
+	uint32_t     delim4, dfold4; /* the 1-byte delimiter, four times (lower case if both cases end a record: dfold4 = 0x20202020) */
 };
 #define FRONT_SMEM (FRONT_NST * FRONT_SLOT_BYTES)
 
@@ -125,7 +125,7 @@ struct OrdParams {
 	const uint8_t *text; uint64_t n;
 	uint16_t *blocks; uint32_t *tiles; const uint64_t *tile_off;
 	agb_record *records; const unsigned long long *totals; uint64_t capacity;
-	uint8_t delim[AGB_MAXDELIM + 2]; int L, kind;
+	uint8_t delim[AGB_MAXDELIM + 2], dfold[AGB_MAXDELIM + 2]; int L, kind;   /* delim: folded (lower case where dfold is 0x20) */
 	long long j0;                /* 0, or -1 when the text starts with the user's delimiter (bitap.c:151-156) */
 };
 

@@ -160,7 +160,7 @@ extern "C" int agb_shard_halo(agb_comm *c, void *d_shard, uint64_t n_local, void
 /* delimiter ends in [0, x) of the local scan, x a multiple of 512, from the block and tile counts the ordinals pass
  * left behind; and the check that a run delimiter ("$$") that reaches the cut begins inside the left halo */
 __global__ void k_shard_aux(const uint8_t *text, const uint16_t *blocks, const uint64_t *tile_off, uint64_t x_lo, uint64_t x_hi, int have_hi,
-                            int kind, int delim0, unsigned long long *out /* [0] S(x_lo), [1] S(x_hi), [2] run error */)
+                            int kind, int delim0, int dfold0, unsigned long long *out /* [0] S(x_lo), [1] S(x_hi), [2] run error */)
 {
 	if (threadIdx.x || blockIdx.x) return;
 	for (int w = 0; w < 2; w++) {
@@ -176,7 +176,7 @@ __global__ void k_shard_aux(const uint8_t *text, const uint16_t *blocks, const u
 	unsigned long long bad = 0;
 	if (kind == 1 && x_lo > 0) {
 		int64_t p = (int64_t)x_lo - 1;
-		while (p >= 0 && text[p] == delim0) p--;
+		while (p >= 0 && (text[p] | dfold0) == delim0) p--;
 		if (p < 0) bad = 1;                                 /* the run covers the whole left halo: where it began is unknown */
 	}
 	out[2] = bad;
@@ -242,7 +242,7 @@ static int shard_scan_geom(const agb_desc &d, const void *d_shard, uint64_t n_lo
 	const bool ord = (want & AGB_WANT_ORDINALS) != 0;
 	const uint64_t x_lo = first ? 0 : halo_left, x_hi = halo_left + n_local;
 	k_shard_aux<<<1, 32, 0, st>>>(text, ord ? W.ord_blocks : nullptr, W.tile_offsets, x_lo, x_hi, open_end ? 0 : 1,
-	                              d.delim_kind, d.delim[0], W.totals + 8);
+	                              d.delim_kind, d.delim[0] | d.delim_fold[0], d.delim_fold[0], W.totals + 8);
 	g_launches++;
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaMemcpyAsync(W.h_totals + 8, W.totals + 8, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));

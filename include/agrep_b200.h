@@ -94,6 +94,11 @@ typedef struct agb_desc {
 	uint32_t anchor3[4];                      /* low three bytes, folded like anchor[] */
 	int32_t  anchor3_off[4];
 	int32_t  adaptive;                        /* 1: the device scan may re-plan the anchors from a sample of the text */
+	/* 0x20 for the delimiter positions that accept both cases of a letter (-i lower-cases the whole internal pattern, the
+	 * delimiter included, maskgen.c:52-58, 259-266), else 0: away from the automaton a delimiter byte c is recognised by
+	 * (c | delim_fold[p]) == (delim[p] | delim_fold[p]); filled by agb_compile / agb_pattern_from_desc from mask[] */
+	uint8_t  delim_fold[2 * AGB_MAXDELIM + 2];
+	uint8_t  pad_[2];
 } agb_desc;
 
 typedef struct agb_pattern agb_pattern;       /* opaque: agb_desc + bookkeeping              */

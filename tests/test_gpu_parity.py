@@ -343,3 +343,27 @@ def test_exact_literal_count_path():
             t = torch.frombuffer(bytearray(data + b"\0" * 64), dtype=torch.uint8).cuda()
             dev = p.scan_device(t.data_ptr(), len(data)).n_matched             # device entry, count only: the exact pass when it applies
             assert got == cnt and dev == cnt, (pat, kw, len(data), got, dev, cnt)
+
+
+@pytest.mark.parametrize("delim", ["X", "ab", "e ", "xx", "Q\\."])
+def test_case_insensitive_delimiters(delim):
+    """-i lower-cases the whole internal pattern, the delimiter included (maskgen.c:52-58, 259-266): -i -d X ends records
+    at 'x' and at 'X'.  The automaton does that by itself; the code that finds delimiters by their bytes (record starts,
+    ordinals, the delimiter counts of stage 1) goes by agb_desc.delim_fold."""
+    rnd = random.Random(9)
+    base = _corpus.make_text(2500, seed=61).decode()
+    raw = delim.replace("\\", "")
+    out = []
+    for ln in base.split("\n"):
+        out.append(ln)
+        out.append(rnd.choice([raw, raw.upper(), raw.lower(), raw.swapcase(), raw + raw.upper()]))
+    data = "".join(out).encode()
+    for pat, kw in (("because", dict(k=1, linenum=1)), ("state good", dict(k=2, linenum=1)), ("the", dict(k=0, linenum=1)),
+                    ("people", dict(k=0, linenum=1, inverse=1)), ("t[hx]e", dict(k=1, linenum=1))):
+        kw = dict(kw, nocase=1, delim=delim)
+        a = _oracle.compile(pat, **kw)
+        for d in (data, raw.upper().encode() + data, data + raw.lower().encode()):
+            cnt, recs = _oracle.scan(a, d)
+            res, got = ag.Pattern(pat, **kw).scan_host(d, ordinals=True)
+            assert res.n_matched == cnt and cnt > 0, (pat, delim)
+            assert [t[:3] for t in got] == list(recs), (pat, delim)
