@@ -55,7 +55,7 @@ class CorpusSpec(C.Structure):
 
 EXPORTS = ["agb_fill_ordinals", "agb_compile", "agb_pattern_free", "agb_pattern_desc", "agb_pattern_from_desc", "agb_scan_device",
            "agb_scan_host", "agb_scan_fd", "agb_bestmatch_device", "agb_corpus_fill_device", "agb_corpus_fill_host",
-           "agb_last_error", "agb_device_count", "agb_set_device", "agb_version", "agb_kernel_launches",
+           "agb_last_error", "agb_device_count", "agb_set_device", "agb_version", "agb_kernel_launches", "agb_shutdown",
            "agb_text_from_host", "agb_text_from_fd", "agb_text_free", "agb_text_size", "agb_text_device", "agb_scan_text",
            "agb_comm_unique_id", "agb_comm_init", "agb_comm_free", "agb_comm_world", "agb_comm_rank", "agb_shard_halo",
            "agb_scan_sharded", "agb_scan_shard_local", "agb_bestmatch_sharded"]

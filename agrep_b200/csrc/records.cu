@@ -373,7 +373,7 @@ k_records_dense(const RecParams P)
 #define LIST_STRIDE (LIST_NG * 4 + 1)                   /* words; odd: the lanes of a warp hit different banks */
 #define LIST_SMEM (REC_THREADS * LIST_STRIDE * 4)
 template <typename T, int NR, bool COSTS>
-__global__ void __launch_bounds__(REC_THREADS)
+__global__ void __launch_bounds__(REC_THREADS, 6)
 k_records_list(const RecParams P)
 {
 	extern __shared__ __align__(16) uint32_t s_win[];
@@ -398,11 +398,16 @@ k_records_list(const RecParams P)
 			int64_t g0 = c - LIST_GB, g1 = c + 1 + LIST_GA;
 			if (g0 < 0) g0 = 0;
 			if (g1 > n_groups) g1 = n_groups;
-			uint4 v[LIST_NG];
+			/* two batches of independent loads (13 groups in one go would hold 52 registers across the whole kernel) */
 #pragma unroll
-			for (int gi = 0; gi < LIST_NG; gi++) if (g0 + gi < g1) v[gi] = __ldg(reinterpret_cast<const uint4 *>(P.text) + g0 + gi);
+			for (int half = 0; half < 2; half++) {
+				constexpr int H = (LIST_NG + 1) / 2;
+				uint4 v[H];
 #pragma unroll
-			for (int gi = 0; gi < LIST_NG; gi++) if (g0 + gi < g1) { strip[gi * 4] = v[gi].x; strip[gi * 4 + 1] = v[gi].y; strip[gi * 4 + 2] = v[gi].z; strip[gi * 4 + 3] = v[gi].w; }
+				for (int gi = 0; gi < H; gi++) { const int g = half * H + gi; if (g < LIST_NG && g0 + g < g1) v[gi] = __ldg(reinterpret_cast<const uint4 *>(P.text) + g0 + g); }
+#pragma unroll
+				for (int gi = 0; gi < H; gi++) { const int g = half * H + gi; if (g < LIST_NG && g0 + g < g1) { strip[g * 4] = v[gi].x; strip[g * 4 + 1] = v[gi].y; strip[g * 4 + 2] = v[gi].z; strip[g * 4 + 3] = v[gi].w; } }
+			}
 			int64_t hi = g1 * 16;
 			if (hi > (int64_t)P.n) hi = (int64_t)P.n;          /* only bytes of the text (the slow path knows the virtual and appended ones) */
 			R.sm = reinterpret_cast<const uint8_t *>(strip); R.lo = g0 * 16; R.len = (uint32_t)(hi - g0 * 16);

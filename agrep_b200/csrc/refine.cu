@@ -103,8 +103,10 @@ static bool refine_geometry(const agb_desc &d, RefineParams &P)
 		}
 		if (!ok) continue;
 		P.hmul = mul;
-		memcpy(P.hidx, slot, sizeof slot);
-		for (int i = 0; i < 16; i++) { P.hval[i] = i < na ? val[i] : 0; P.hmask[i] = i < na ? msk[i] : 0; P.hoffs[i] = i < na ? (int8_t)off[i] : 0; }
+		memcpy(P.hidx64, slot, sizeof slot);
+		int8_t offs8[16];
+		for (int i = 0; i < 16; i++) { P.hval[i] = i < na ? val[i] : 0; P.hmask[i] = i < na ? msk[i] : 0; offs8[i] = i < na ? (int8_t)off[i] : 0; }
+		memcpy(P.hoffs64, offs8, sizeof offs8);
 		return true;
 	}
 	return false;

@@ -13,7 +13,25 @@
 /* the hit windows of a chunk: bit s of the result = some anchor starts at byte s.  Stage 1's polynomial over the
  * 16 windows (IMADs on the FMA pipe); f == 0 is folded into a bit per window without a compare: min(f, 1) shifted
  * into the mask by a multiply-add.  x[0..4]: the chunk and the word that follows it, case-folded like stage 1 does. */
-template <int NA, bool SCALED, int N3 = 0>
+struct AnchorTable { int8_t idx[32]; uint32_t val[16], mask[16]; int8_t off[16]; int n; };
+/* mixed plans (four-byte and three-byte anchors; rare): every window against every anchor under that anchor's mask, from
+ * the table in shared memory */
+__device__ __forceinline__ uint32_t hit_windows_tab(const uint32_t (&x)[5], const AnchorTable &A)
+{
+	uint32_t hits = 0;
+#pragma unroll
+	for (int w = 0; w < 4; w++) {
+		const uint32_t wv[4] = { x[w], __funnelshift_r(x[w], x[w + 1], 8), __funnelshift_r(x[w], x[w + 1], 16), __funnelshift_r(x[w], x[w + 1], 24) };
+		for (int a = 0; a < A.n; a++) {
+			const uint32_t V = A.val[a], M = A.mask[a];
+#pragma unroll
+			for (int j = 0; j < 4; j++) if ((wv[j] & M) == V) hits |= 1u << (4 * w + j);
+		}
+	}
+	return hits;
+}
+
+template <int NA, bool SCALED>
 __device__ __forceinline__ uint32_t hit_windows_poly(const uint32_t (&x)[5], const RefineParams &P)
 {
 	uint32_t wv[16];
@@ -29,12 +47,6 @@ __device__ __forceinline__ uint32_t hit_windows_poly(const uint32_t (&x)[5], con
 #pragma unroll
 		for (int i = NA - 2; i >= 0; i--) r = r * wv[s] + P.coef[i];
 		if (SCALED) r *= P.scale;
-		if (N3 > 0) {                                        /* mixed plan: the three-byte group's polynomial, scaled by 256 */
-			uint32_t q = wv[s] * P.one + P.coef3[N3 - 1];
-#pragma unroll
-			for (int i = N3 - 2; i >= 0; i--) q = q * wv[s] + P.coef3[i];
-			r = min(r, q * 256u);
-		}
 		nz = nz * 2u + min(r, 1u);
 	}
 	return ~nz & 0xFFFFu;
@@ -65,24 +77,8 @@ __device__ __forceinline__ uint32_t hit_windows_na(const uint32_t (&x)[5], const
 	default: return hit_windows_poly<9, SCALED>(x, P);
 	}
 }
-__device__ __forceinline__ uint32_t hit_windows_mixed(const uint32_t (&x)[5], const RefineParams &P)
-{
-	if (P.n3 == 1) switch (P.na) {
-	case 1: return hit_windows_poly<1, false, 1>(x, P);  case 2: return hit_windows_poly<2, false, 1>(x, P);
-	case 3: return hit_windows_poly<3, false, 1>(x, P);  case 4: return hit_windows_poly<4, false, 1>(x, P);
-	case 5: return hit_windows_poly<5, false, 1>(x, P);  case 6: return hit_windows_poly<6, false, 1>(x, P);
-	default: return hit_windows_poly<7, false, 1>(x, P);
-	}
-	switch (P.na) {
-	case 1: return hit_windows_poly<1, false, 2>(x, P);  case 2: return hit_windows_poly<2, false, 2>(x, P);
-	case 3: return hit_windows_poly<3, false, 2>(x, P);  case 4: return hit_windows_poly<4, false, 2>(x, P);
-	case 5: return hit_windows_poly<5, false, 2>(x, P);  case 6: return hit_windows_poly<6, false, 2>(x, P);
-	default: return hit_windows_poly<7, false, 2>(x, P);
-	}
-}
 __device__ __forceinline__ uint32_t hit_windows(const uint32_t (&x)[5], const RefineParams &P)
 {
-	if (P.n3) return hit_windows_mixed(x, P);
 	if (!P.poly) return hit_windows_cmp(x, P);
 	return P.scale != 1 ? hit_windows_na<true>(x, P) : hit_windows_na<false>(x, P);
 }
@@ -91,7 +87,6 @@ __device__ __forceinline__ uint32_t hit_windows(const uint32_t (&x)[5], const Re
  * (p0 = 16 * chunk + code - 32).  cw: the chunk's words in the lane's strip.  Which anchor it is: a multiplicative hash
  * of the window's bytes picks a slot (the host found a multiplier that keeps the anchors apart); the four-byte reading
  * of the window is tried first, then (mixed plans) the three-byte one. */
-struct AnchorTable { int8_t idx[32]; uint32_t val[16], mask[16]; int8_t off[16]; };
 __device__ __forceinline__ uint32_t start_code(const uint32_t *cw, const int s, const RefineParams &P, const AnchorTable &A)
 {
 	const uint32_t lo = cw[s >> 2] | P.fold, hi = cw[(s >> 2) + 1] | P.fold;
@@ -214,8 +209,16 @@ k_refine(const RefineParams P)
 	__shared__ uint32_t s_ring2[REFINE_THREADS / 32][REFINE_RING2];
 	__shared__ uint32_t s_ring3[REFINE_THREADS / 32][REFINE_RING3];
 	__shared__ AnchorTable s_offs;
-	if (threadIdx.x < 32) s_offs.idx[threadIdx.x] = P.hidx[threadIdx.x];
-	if (threadIdx.x < 16) { s_offs.val[threadIdx.x] = P.hval[threadIdx.x]; s_offs.mask[threadIdx.x] = P.hmask[threadIdx.x]; s_offs.off[threadIdx.x] = P.hoffs[threadIdx.x]; }
+	if (threadIdx.x == 0) {
+		/* (static indexes: a kernel parameter indexed by a run-time value is copied to local memory as a whole, and every
+		 * later P.x would be a local load) */
+#pragma unroll
+		for (int i = 0; i < 32; i++) s_offs.idx[i] = (int8_t)(P.hidx64[i >> 3] >> (8 * (i & 7)));
+#pragma unroll
+		s_offs.n = P.na + P.n3;
+#pragma unroll
+		for (int i = 0; i < 16; i++) { s_offs.val[i] = P.hval[i]; s_offs.mask[i] = P.hmask[i]; s_offs.off[i] = (int8_t)(P.hoffs64[i >> 3] >> (8 * (i & 7))); }
+	}
 	DevConsts<T> C;
 	shared_init<T, NR>(SH, C, P.desc, REFINE_THREADS);
 	const T init0 = mirror<T>((T)P.desc->init0);
@@ -312,7 +315,7 @@ k_refine(const RefineParams P)
 		uint32_t hits = 0;
 		if (run) {
 			const uint32_t x[5] = { cw[0] | P.fold, cw[1] | P.fold, cw[2] | P.fold, cw[3] | P.fold, cw[4] | P.fold };
-			hits = hit_windows(x, P);
+			hits = P.n3 ? hit_windows_tab(x, s_offs) : hit_windows(x, P);
 			hits &= hits - 1;                                 /* the first one has been judged */
 		}
 		uint32_t seen1 = first, seen2 = first;
@@ -357,7 +360,7 @@ k_refine(const RefineParams P)
 		uint32_t hits = 0, code = 0;
 		if (crun) {
 			const uint32_t x[5] = { cw[0] | P.fold, cw[1] | P.fold, cw[2] | P.fold, cw[3] | P.fold, cw[4] | P.fold };
-			hits = hit_windows(x, P);
+			hits = P.n3 ? hit_windows_tab(x, s_offs) : hit_windows(x, P);
 			if (hits) code = start_code(cw, __ffs(hits) - 1, P, s_offs);
 		}
 		count_push(crel, code, hits != 0);

@@ -31,6 +31,28 @@ std::atomic<uint64_t> g_launches{0};
 extern "C" const char *agb_last_error(void) { return g_err; }
 extern "C" const char *agb_version(void) { return "agrep-b200 0.1 (sm_100a)"; }
 extern "C" uint64_t agb_kernel_launches(void) { return g_launches.load(); }
+/* frees the per-device scratch of this process (bitmaps, candidate lists, pinned rings, streams, events); the next
+ * scan allocates again */
+extern "C" void agb_shutdown(void)
+{
+	int cur = 0; cudaGetDevice(&cur);
+	for (int dev = 0; dev < 64; dev++) {
+		std::lock_guard<std::mutex> lk(g_ws_mu[dev]);
+		Workspace &W = g_ws[dev];
+		if (!W.totals && !W.bitmap && !W.h2d_text) continue;
+		if (cudaSetDevice(dev) != cudaSuccess) { cudaGetLastError(); continue; }
+		cudaDeviceSynchronize();
+		cudaFree(W.bitmap); cudaFree(W.bitmap2); cudaFree(W.range_counts); cudaFree(W.range_offsets);
+		cudaFree(W.tile_counts); cudaFree(W.tile_offsets); cudaFree(W.cand); cudaFree(W.cand_counts); cudaFree(W.cand_offsets);
+		cudaFree(W.cand_first); cudaFree(W.scan_sums); cudaFree(W.scan_offs); cudaFree(W.ord_blocks); cudaFree(W.totals);
+		cudaFreeHost(W.h_totals); cudaFree(W.d_desc); cudaFree(W.h2d_text); cudaFree(W.h2d_rec); cudaFree(W.d_gram); cudaFreeHost(W.h_gram);
+		if (W.e0) cudaEventDestroy(W.e0); if (W.e1) cudaEventDestroy(W.e1); if (W.e2) cudaEventDestroy(W.e2);
+		for (int i = 0; i < STAGE_BUFS; i++) { if (W.ev_copy[i]) cudaEventDestroy(W.ev_copy[i]); if (W.stage[i]) cudaFreeHost(W.stage[i]); }
+		if (W.s_copy) cudaStreamDestroy(W.s_copy); if (W.s_comp) cudaStreamDestroy(W.s_comp);
+		W = Workspace();
+	}
+	cudaSetDevice(cur);
+}
 extern "C" int agb_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 extern "C" int agb_set_device(int dev) { CUDA_TRY(cudaSetDevice(dev)); return AGB_OK; }
 
@@ -39,7 +61,7 @@ extern "C" int agb_set_device(int dev) { CUDA_TRY(cudaSetDevice(dev)); return AG
  * ============================================================================================== */
 
 Workspace g_ws[64];
-std::mutex g_ws_mu;
+std::mutex g_ws_mu[64];          /* one scan at a time per DEVICE (its workspace is shared scratch); different devices run side by side */
 
 static int ws_prepare(Workspace &W, uint64_t n)
 {
@@ -297,7 +319,8 @@ static int adaptive_plan(const agb_desc &d, Workspace &W, const void *d_text, ui
 	 * of the chunks instead of 4.5 %), stage 1 ran 22 % longer (14.5 instead of 11.8 ms per 64 GiB: the second polynomial
 	 * and one VIMNMX3 per window instead of half of one) and stage 1.5 did not get cheaper in proportion -- a mixed plan
 	 * only pays when the four-byte grams of a piece are really common */
-	const double INF = 1e30, MIXED = 0.03;
+	const char *mp = getenv("AGB_PLAN_MIXED");           /* (tests force mixed plans with AGB_PLAN_MIXED=0) */
+	const double INF = 1e30, MIXED = mp ? atof(mp) : 0.03;
 	static double f[66][10][3]; static int from[66][10][3];   /* gram taken to get here, -1: position skipped */
 	for (int p = 0; p <= d.pat_len; p++) for (int j = 0; j <= need; j++) for (int t = 0; t < 3; t++) { f[p][j][t] = INF; from[p][j][t] = -2; }
 	f[0][0][0] = 0;
@@ -394,7 +417,7 @@ int scan_device_impl(const agb_desc &d_in, const void *d_text, uint64_t n, int w
 	if ((want & AGB_WANT_RECORDS) && capacity && !d_records) return AGB_ERR_ARG;
 	int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
 	if (dev < 0 || dev >= 64) return AGB_ERR_ARG;
-	std::lock_guard<std::mutex> lk(g_ws_mu);
+	std::lock_guard<std::mutex> lk(g_ws_mu[dev]);
 	Workspace &W = g_ws[dev];
 	int rc = ws_prepare(W, n); if (rc) return rc;
 	agb_desc planned;
@@ -465,7 +488,7 @@ static int scan_stream_impl(const agb_desc &d, uint64_t n, const SliceSource &sr
 	memset(res, 0, sizeof *res);
 	int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
 	if (dev < 0 || dev >= 64) return AGB_ERR_ARG;
-	std::lock_guard<std::mutex> lk(g_ws_mu);
+	std::lock_guard<std::mutex> lk(g_ws_mu[dev]);
 	Workspace &W = g_ws[dev];
 	int rc = ws_prepare(W, n); if (rc) return rc;
 	if (!W.s_copy) {
@@ -588,7 +611,7 @@ static int text_upload(const SliceSource &src, uint64_t n, agb_text **out)
 	agb_text *t = new agb_text; t->d = nullptr; t->n = n; t->dev = dev;
 	const size_t need = (size_t)((n + 15) / 16 * 16 + 4096);
 	if (cudaMalloc(&t->d, need) != cudaSuccess) { delete t; snprintf(g_err, sizeof g_err, "cudaMalloc of %zu bytes for the text failed", need); cudaGetLastError(); return AGB_ERR_NOMEM; }
-	std::lock_guard<std::mutex> lk(g_ws_mu);
+	std::lock_guard<std::mutex> lk(g_ws_mu[dev]);
 	Workspace &W = g_ws[dev];
 	int rc = ws_prepare(W, 0); if (rc) { cudaFree(t->d); delete t; return rc; }
 	if (!W.s_copy) {
@@ -659,7 +682,7 @@ static int scan_text_impl(const agb_desc &d, const agb_text *t, int want, int wa
 	CUDA_TRY(cudaSetDevice(t->dev));
 	agb_record *d_rec = nullptr;
 	{
-		std::lock_guard<std::mutex> lk(g_ws_mu);
+		std::lock_guard<std::mutex> lk(g_ws_mu[t->dev]);
 		Workspace &W = g_ws[t->dev];
 		if ((want & AGB_WANT_RECORDS) && capacity > W.h2d_rec_cap) {
 			if (W.h2d_rec) cudaFree(W.h2d_rec);
@@ -752,7 +775,7 @@ extern "C" int agb_bestmatch_device(const char *pattern, const agb_options *opt,
 				res->n_records = r2.n_records; res->truncated = r2.truncated;
 			} else if (best < k && res->n_records) {
 				int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
-				std::lock_guard<std::mutex> lk(g_ws_mu);
+				std::lock_guard<std::mutex> lk(g_ws_mu[dev]);
 				Workspace &W = g_ws[dev];
 				k_filter_level<<<1, 1024, 0, st>>>(d_records, res->n_records, best, W.totals + 15); g_launches++;
 				CUDA_TRY(cudaGetLastError());

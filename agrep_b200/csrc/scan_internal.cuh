@@ -69,8 +69,9 @@ struct RefineParams {
 	uint32_t coef[AGB_MAXANCHOR]; uint32_t one, scale; int poly;   /* stage 1's polynomial, to spot the candidate windows cheaply */
 	int t1, t1_words;            /* the band count: usable; words of the window [p0 - k, p0 + pat_len + k) */
 	uint32_t t1_fold, t1_pat[16], t1_care[16];   /* literal pattern bytes (little endian words), 0x80 per literal position */
-	uint32_t hmul; int8_t hidx[32];              /* anchor bytes -> anchor: slot (bytes * hmul) >> 27 holds its index + 1 */
-	uint32_t hval[16], hmask[16]; int8_t hoffs[16];   /* the anchors of both groups: bytes, mask (4 or 3 bytes), off */
+	uint32_t hmul; uint64_t hidx64[4];           /* anchor bytes -> anchor: slot (bytes * hmul) >> 27 holds its index + 1 (32 bytes, packed:
+	                                                byte arrays in a kernel parameter get the whole struct copied to local memory) */
+	uint32_t hval[16], hmask[16]; uint64_t hoffs64[2];   /* the anchors of both groups: bytes, mask (4 or 3 bytes), off (16 bytes, packed) */
 	int n3; uint32_t coef3[4];                   /* mixed plan: the three-byte group's polynomial */
 	int sm_count;
 };
@@ -173,7 +174,7 @@ struct Workspace {               /* grow-only device scratch, one per device */
 /* scan.cu */
 #include <mutex>
 extern Workspace g_ws[64];
-extern std::mutex g_ws_mu;       /* one scan at a time per process (the workspaces are shared scratch) */
+extern std::mutex g_ws_mu[64];   /* one scan at a time per device (the workspaces are shared scratch) */
 int  scan_device_impl(const agb_desc &d, const void *d_text, uint64_t n, int want, int want_level,
                       agb_record *d_records, uint64_t capacity, cudaStream_t st, agb_result *res, const ShardInfo *sh = nullptr);
 /* front.cu */

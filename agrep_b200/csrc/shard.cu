@@ -237,7 +237,7 @@ static int shard_scan_geom(const agb_desc &d, const void *d_shard, uint64_t n_lo
 	memset(part, 0, sizeof *part);
 	int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
 	/* the delimiter counts of the halos (ordinals) and the run check of the left halo */
-	std::lock_guard<std::mutex> lk(g_ws_mu);
+	std::lock_guard<std::mutex> lk(g_ws_mu[dev]);
 	Workspace &W = g_ws[dev];
 	const bool ord = (want & AGB_WANT_ORDINALS) != 0;
 	const uint64_t x_lo = first ? 0 : halo_left, x_hi = halo_left + n_local;
@@ -404,7 +404,7 @@ extern "C" int agb_bestmatch_sharded(const char *pattern, const agb_options *opt
 				rc = agbi_build(pattern, &o, &d, err, errlen); if (rc) return rc;
 				rc = shard_local_scan(d, c, d_shard, n_local, want, best, capacity, st, &lres); if (rc) return rc;
 			} else if (best < k && lres.n_records) {
-				std::lock_guard<std::mutex> lk(g_ws_mu);
+				std::lock_guard<std::mutex> lk(g_ws_mu[c->dev]);
 				Workspace &W = g_ws[c->dev];
 				k_filter_level<<<1, 1024, 0, st>>>(c->d_local, lres.n_records, best, W.totals + 15); g_launches++;
 				CUDA_TRY(cudaGetLastError());

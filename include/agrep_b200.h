@@ -244,6 +244,7 @@ const char *agb_last_error(void);
 int  agb_device_count(void);
 int  agb_set_device(int dev);
 const char *agb_version(void);
+void agb_shutdown(void);              /* frees the library's per-device scratch (scans of different devices run side by side; one at a time per device) */
 uint64_t agb_kernel_launches(void);   /* kernels this process launched through the library so far */
 
 #ifdef __cplusplus

@@ -64,3 +64,44 @@ def test_the_record_stage_gets_few_chunks_when_the_filters_can_thin():
         assert res.n_flagged < chunks // 20, (pat, kw, res.n_flagged, chunks)
     res, _ = ag.Pattern("the").scan_host(host, want_records=False)
     assert res.n_flagged == chunks
+
+
+def test_anchor_planner_plans_agree(monkeypatch):
+    """the anchor planner (scan.cu: grams counted on a sample of the text, k+1 disjoint grams by dynamic program) only
+    changes which chunks stage 1 flags, never the answer: the static plan (small texts), the planned one and a forced
+    mixed plan (four-byte + three-byte anchors: two polynomials in stage 1, table compare in stage 1.5) return the same
+    ordered list on a 320 MiB text, and a window of it equals the oracle's"""
+    import torch
+    n = 320 << 20
+    t = torch.empty(n + 4096, dtype=torch.uint8, device="cuda")
+    t[n:].zero_()
+    ag.corpus_device(t.data_ptr(), n, needle="because each", needle_every=512, needle_maxedits=3)
+    torch.cuda.synchronize()
+    cap = 1 << 20
+    lists = []
+    for env in (None, "0", "10"):
+        if env is None:
+            monkeypatch.delenv("AGB_PLAN_MIXED", raising=False)
+        else:
+            monkeypatch.setenv("AGB_PLAN_MIXED", env)
+        for pat, kw in (("because each", dict(k=2)), ("because each just those", dict(k=3, nocase=True, linenum=True)),
+                        ("government of the people", dict(k=2, linenum=True))):
+            rec = torch.zeros((cap, 4), dtype=torch.int64, device="cuda")
+            # a fresh text pointer per setting would defeat nothing: the plan is cached per (descriptor, text); change k's
+            # sibling field instead -- a new Pattern object has the same descriptor, so shift the text by one page
+            off = {None: 0, "0": 4096, "10": 8192}[env]
+            r = ag.Pattern(pat, **kw).scan_device(t.data_ptr() + off, n - 16384, d_records=rec.data_ptr(), capacity=cap)
+            lists.append((env, pat, off, int(r.n_matched), (rec[:r.n_records, :2] + off).cpu()))
+    import _oracle
+    by_pat = {}
+    for env, pat, off, cnt, l in lists:
+        by_pat.setdefault(pat, []).append((env, off, cnt, l))
+    for pat, runs in by_pat.items():
+        # the three texts overlap in [8192, n - 16384): same records there
+        def inside(l):
+            m = (l[:, 0] >= 8192 + 4096) & (l[:, 1] < n - 16384 - 4096)
+            return l[m]
+        base = inside(runs[0][3])
+        assert base.shape[0] > 10, pat
+        for env, off, cnt, l in runs[1:]:
+            assert bool((inside(l) == base).all()), (pat, env)

@@ -115,3 +115,41 @@ def test_memory_mode_through_the_dropin(files, args, name):
     r = run(MEM, [files[name], "-V0"] + args)
     d = run(MEMDROP, [files[name], "-V0"] + args)
     assert d[1] == r[1] and d[0] == r[0]
+
+
+def test_three_gib_file_streams_through_the_dropin(tmp_path):
+    """`agrep_dropin -c` on a file of 3 GiB (past the reference's 2 GiB `int` offsets): the file is read(2) straight into
+    the pinned ring and on to the device, never slurped -- same count as the unmodified reference, resident set far below
+    the file size.  Skipped where the scratch disk or the page cache cannot hold the file."""
+    import resource, shutil, sys
+    sys.path.insert(0, ROOT)
+    import agrep_b200 as ag
+    if not (os.path.exists(REF) and os.path.exists(DROP)):
+        pytest.skip("oracle/_ref binaries not built")
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > (5 << 30) else str(tmp_path)
+    if shutil.disk_usage(base).free < (4 << 30):
+        pytest.skip("no room for a 3 GiB file")
+    path = os.path.join(base, "agb_big_%d.txt" % os.getpid())
+    piece, total = 256 << 20, 3 << 30
+    try:
+        with open(path, "wb") as f:
+            for i in range(total // piece):
+                f.write(ag.corpus_host(piece, first_page=i * (piece // 4096), needle="because each", needle_every=512, needle_maxedits=3))
+        for args in (["-c", "-n", "-2", "because each"], ["-c", "government"]):
+            r = subprocess.run([REF, "-V0"] + args + [path], capture_output=True, timeout=900)
+            before = resource.getrusage(resource.RUSAGE_CHILDREN).ru_maxrss
+            d = subprocess.run([DROP, "-V0"] + args + [path], capture_output=True, timeout=900)
+            rss_kib = resource.getrusage(resource.RUSAGE_CHILDREN).ru_maxrss
+            assert d.stdout == r.stdout and int(d.stdout.split()[0]) > 1000, (args, d.stdout, r.stdout, d.stderr[-300:])
+            # ru_maxrss of the children is a running maximum: the reference (48 KiB buffers) keeps it small, so what shows
+            # is the drop-in; CUDA context + pinned ring + libraries, not the file
+            assert max(rss_kib, before) * 1024 < 0.8 * total, rss_kib          # (measured: 2.0 GB, CUDA context and module included)
+        # records past 2 GiB come out with the right bytes: the last matching lines of the file, as the reference prints them
+        r = subprocess.run("%s -V0 -2 'because each' %s | tail -c 4096" % (REF, path), shell=True, capture_output=True, timeout=900)
+        d = subprocess.run("%s -V0 -2 'because each' %s | tail -c 4096" % (DROP, path), shell=True, capture_output=True, timeout=900)
+        assert d.stdout == r.stdout and len(d.stdout) > 100
+    finally:
+        try:
+            os.unlink(path)
+        except OSError:
+            pass
