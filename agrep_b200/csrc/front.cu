@@ -229,91 +229,71 @@ __device__ __forceinline__ uint32_t eq_bytes(uint32_t x, uint32_t c4)
 }
 
 template <bool MASKED, bool FOLD, bool FULL>
-__device__ __forceinline__ void exact_chunks(const FrontParams &P, const uint8_t *st, uint32_t tid, uint32_t lane, uint32_t rem, uint32_t *bm, uint64_t stage_byte0)
+__device__ __forceinline__ void exact_chunks(const FrontParams &P, const uint8_t *st, uint32_t tid, uint32_t lane, uint32_t rem, uint32_t *bmw, uint64_t stage_byte0)
 {
 	const uint32_t lt = (1u << lane) - 1u;
+	static_assert(FRONT_CH % 2 == 0, "a lane takes two adjacent chunks");
 #pragma unroll 1
-	for (int c = 0; c < FRONT_CH; c++) {
-		const uint32_t idx = c * FRONT_THREADS + tid;
-		const uint4 v = *reinterpret_cast<const uint4 *>(st + idx * 16);
-		const uint32_t x4 = *reinterpret_cast<const uint32_t *>(st + idx * 16 + 16);
-		const uint32_t raw[5] = { v.x, v.y, v.z, v.w, x4 };
-		uint32_t x[5];
+	for (int c = 0; c < FRONT_CH / 2; c++) {
+		/* a lane takes 32 consecutive bytes (two chunks), a warp 1 KiB = two summary words: the stitching below is paid once
+		 * per 32 bytes */
+		const uint32_t idx = 2 * (c * FRONT_THREADS + tid);
+		const uint4 v0 = *reinterpret_cast<const uint4 *>(st + idx * 16);
+		const uint4 v1 = *reinterpret_cast<const uint4 *>(st + idx * 16 + 16);
+		const uint32_t x8 = *reinterpret_cast<const uint32_t *>(st + idx * 16 + 32);
+		const uint32_t raw[9] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, x8 };
+		/* one bit per byte position, no branches: hm = windows that equal the literal, nm = delimiter bytes.  Both tests are
+		 * "a scaled difference is zero" (IMAD), turned into a bit by min(.,1) and shifted in by a multiply-add: 4 FMA-pipe and
+		 * 2.75 ALU-pipe instructions per window.  Windows run backwards so that byte 0 ends up in bit 0. */
+		uint32_t ah = 0, ad = 0;
 #pragma unroll
-		for (int i = 0; i < 5; i++) x[i] = FOLD ? (raw[i] | P.fold) : raw[i];
-		/* any window == the anchor?  (one anchor: the unsigned minimum of the differences) */
-		uint32_t acc = 0xffffffffu;
+		for (int w = 7; w >= 0; w--) {
+			const uint32_t wv[4] = { raw[w], __funnelshift_r(raw[w], raw[w + 1], 8), __funnelshift_r(raw[w], raw[w + 1], 16), __funnelshift_r(raw[w], raw[w + 1], 24) };
 #pragma unroll
-		for (int w = 0; w < 4; w++) {
-			uint32_t wv[4] = { x[w], __funnelshift_r(x[w], x[w + 1], 8), __funnelshift_r(x[w], x[w + 1], 16), __funnelshift_r(x[w], x[w + 1], 24) };
-#pragma unroll
-			for (int j = 0; j < 4; j++) { const uint32_t dlt = (MASKED ? (wv[j] & P.amask) : wv[j]) - P.anchor[0]; wv[j] = dlt; }
-			acc = __vimin3_u32(acc, wv[0], wv[1]);
-			acc = __vimin3_u32(acc, wv[2], wv[3]);
-		}
-		bool hit = acc == 0;
-		/* a delimiter byte in the chunk? */
-		uint32_t z = 0;
-#pragma unroll
-		for (int w = 0; w < 4; w++) { const uint32_t t = raw[w] ^ P.delim4; z |= (t - 0x01010101u) & ~t; }
-		bool nl = (z & 0x80808080u) != 0;
-		uint32_t lead = 0, trail = 0, inner = 0;        /* of a chunk with a hit: delimiter before its first hit / after its last; hits that follow a delimiter inside it */
-		const int64_t base = (int64_t)stage_byte0 + (int64_t)idx * 16;
-		const bool tail = !FULL && (idx >= rem || base + 16 + 4 > (int64_t)P.n);
-		if (!FULL && idx >= rem) { hit = false; nl = false; }
-		uint32_t T = 0, L = 0, I = 0;                      /* ballots of trail / lead, sum of inner: only chunks that took the byte-position path have any */
-		if (__any_sync(0xffffffffu, (hit && nl) || (tail && (hit || nl)))) {
-			if ((hit && nl) || (tail && (hit || nl))) {
-				/* byte positions: hm = windows that equal the anchor, nm = delimiter bytes (both cut at the end of the text) */
-				uint32_t hm = 0, nm = 0;
-#pragma unroll
-				for (int w = 0; w < 4; w++) {
-					const uint32_t wv[4] = { x[w], __funnelshift_r(x[w], x[w + 1], 8), __funnelshift_r(x[w], x[w + 1], 16), __funnelshift_r(x[w], x[w + 1], 24) };
-#pragma unroll
-					for (int j = 0; j < 4; j++) if ((MASKED ? (wv[j] & P.amask) : wv[j]) == P.anchor[0]) hm |= 1u << (4 * w + j);
-					const uint32_t e = eq_bytes(raw[w], P.delim4);
-					nm |= ((((e >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * w);
-				}
-				if (tail) {
-					const int64_t nb = (int64_t)P.n - base;                 /* bytes of the text in this chunk */
-					const int64_t nh = nb - (int64_t)P.alen + 1;             /* windows that lie inside the text */
-					nm &= nb >= 16 ? 0xFFFFu : (nb <= 0 ? 0u : ((1u << nb) - 1u));
-					hm &= nh >= 16 ? 0xFFFFu : (nh <= 0 ? 0u : ((1u << nh) - 1u));
-					hit = hm != 0; nl = nm != 0;
-				}
-				if (hit) {
-					const int first = __ffs(hm) - 1, last = 31 - __clz(hm);
-					lead = (nm & ((1u << first) - 1u)) ? 1u : 0u;
-					trail = (nm >> last) > 1u ? 1u : 0u;                  /* a delimiter after the last hit's first byte (it cannot be inside the hit) */
-					for (uint32_t h = hm & (hm - 1); h; h &= h - 1) {       /* hits after the first: a delimiter since the hit before? */
-						const int cur = __ffs(h) - 1, prev = 31 - __clz(hm & ((1u << cur) - 1u));
-						inner += (nm & ((1u << cur) - 1u) & ~((2u << prev) - 1u)) ? 1u : 0u;
-					}
-				}
+			for (int j = 3; j >= 0; j--) {
+				const uint32_t dh = (FOLD ? (wv[j] | P.fold) : wv[j]) * P.scale - P.coef[0];   /* zero iff the low alen bytes are the literal */
+				const uint32_t dd = wv[j] * P.coef3[2] - P.coef3[1];                            /* zero iff the low byte is the delimiter */
+				ah = ah * P.coef3[0] + __vimin3_u32(dh, 1u, 1u);
+				ad = ad * P.coef3[0] + __vimin3_u32(dd, 1u, 1u);
 			}
-			T = __ballot_sync(0xffffffffu, trail != 0);
-			L = __ballot_sync(0xffffffffu, lead != 0);
-			I = __reduce_add_sync(0xffffffffu, inner);
 		}
-		const uint32_t A = __ballot_sync(0xffffffffu, hit);
-		const uint32_t N = __ballot_sync(0xffffffffu, nl && !hit);          /* delimiters in chunks without a hit */
-		/* this hit starts a new record (within the warp's 512 bytes) if a delimiter lies between it and the hit before */
-		bool fresh = false;
-		if (hit && (A & lt)) {
-			const int j = 31 - __clz(A & lt);
-			fresh = lead || ((T >> j) & 1u) || (N & lt & ~((2u << j) - 1u));
-		}
-		const uint32_t F = __ballot_sync(0xffffffffu, fresh);
-		if (lane == 0 && (FULL || idx < rem)) {
-			uint32_t sum = __popc(F) + I;
-			if (A) {
-				const int fi = __ffs(A) - 1, la = 31 - __clz(A);
-				sum |= EX_HAS;
-				if (((L >> fi) & 1u) || (N & ((1u << fi) - 1u))) sum |= EX_LEAD;
-				if (((T >> la) & 1u) || (la < 31 && (N >> (la + 1)))) sum |= EX_TRAIL;
+		uint32_t hm = ~ah, nm = ~ad;
+		if (!FULL) {
+			const int64_t nb = (int64_t)P.n - ((int64_t)stage_byte0 + (int64_t)idx * 16);   /* bytes of the text in these 32 */
+			if (nb < 32 + 4) {
+				const int64_t nh = nb - (int64_t)P.alen + 1;                                /* windows that lie inside the text */
+				nm &= nb >= 32 ? 0xFFFFFFFFu : (nb <= 0 ? 0u : ((1u << nb) - 1u));
+				hm &= nh >= 32 ? 0xFFFFFFFFu : (nh <= 0 ? 0u : ((1u << nh) - 1u));
 			}
-			if (N || L || T || __popc(F) || I) sum |= EX_ANY;
-			bm[c * (FRONT_THREADS / 32)] = sum;
+		}
+		/* a hit counts if it is the first since the last delimiter.  Across lanes by ballots: has a hit been seen since the
+		 * last delimiter before these bytes (within the warp's 1 KiB)? */
+		const uint32_t Hb = __ballot_sync(0xffffffffu, hm != 0), Db = __ballot_sync(0xffffffffu, nm != 0);
+		const uint32_t Tb = __ballot_sync(0xffffffffu, nm != 0 && hm > nm);      /* a hit after the lane's last delimiter */
+		const uint32_t pd = Db & lt;
+		uint32_t seen;
+		if (pd) { const int p = 31 - __clz(pd); seen = ((Tb >> p) & 1u) | ((Hb & lt & ~((2u << p) - 1u)) ? 1u : 0u); }
+		else seen = (Hb & lt) ? 1u : 0u;
+		/* inside the lane by one subtraction: a borrow started at every record start (the bit after a delimiter; bit 0 unless
+		 * a hit has been seen) runs up to the first hit or delimiter of that record and clears it (or leaves at the top) */
+		const uint32_t ev = hm | nm;
+		const uint32_t first = ev & ~(ev - ((nm << 1) | (seen ^ 1u))) & hm;
+		const uint32_t Fs = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(first));
+		const uint32_t Lb = __ballot_sync(0xffffffffu, hm != 0 && (nm & ((hm & (0u - hm)) - 1u)) != 0);   /* a delimiter before the lane's first hit */
+		const uint32_t Gb = __ballot_sync(0xffffffffu, hm != 0 && nm > hm);                                /* ... after its last hit */
+		if (lane == 0) {
+			uint32_t sum = 0;
+			if (Hb) {
+				const int fi = __ffs(Hb) - 1, la = 31 - __clz(Hb);
+				sum = (Fs - 1u) | EX_HAS;
+				if (((Lb >> fi) & 1u) || (Db & ((1u << fi) - 1u))) sum |= EX_LEAD;
+				if (((Gb >> la) & 1u) || (la < 31 && (Db >> (la + 1)))) sum |= EX_TRAIL;
+			}
+			if (Db) sum |= EX_ANY;
+			/* the summary of the 1 KiB in its first word, the identity in the second */
+			const uint32_t word = idx / 32;
+			if (FULL || idx < rem) bmw[word] = sum;
+			if (FULL || idx + 32 < rem) bmw[word + 1] = 0;
 		}
 	}
 }
@@ -340,7 +320,6 @@ k_front_exact(const FrontParams P)
 		bulk_g2s(s_ring + slot * FRONT_SLOT_BYTES, P.text + off, bytes, &s_bar[slot]);
 	};
 	if (tid == 0) for (int i = 0; i < FRONT_NST; i++) issue(i);
-	const uint32_t warp_in_cta = tid >> 5;
 	for (uint32_t it = 0;; it++) {
 		const uint64_t sg = P.stage_begin + blockIdx.x + (uint64_t)it * gridDim.x;
 		if (sg >= P.stage_end) break;
@@ -349,10 +328,10 @@ k_front_exact(const FrontParams P)
 		const uint8_t *st = s_ring + slot * FRONT_SLOT_BYTES;
 		const uint64_t left = P.n_chunks - sg * FRONT_STAGE_CHUNKS;
 		const uint32_t rem = left > 0xFFFF0000ull ? 0xFFFF0000u : (uint32_t)left;
-		uint32_t *bm = P.bitmap + sg * FRONT_WORDS_PER_STAGE + warp_in_cta;
+		uint32_t *bmw = P.bitmap + sg * FRONT_WORDS_PER_STAGE;
 		const bool full = left >= FRONT_STAGE_CHUNKS + 2;
-		if (full) exact_chunks<MASKED, FOLD, true>(P, st, tid, lane, rem, bm, sg * FRONT_STAGE_BYTES);
-		else exact_chunks<MASKED, FOLD, false>(P, st, tid, lane, rem, bm, sg * FRONT_STAGE_BYTES);
+		if (full) exact_chunks<MASKED, FOLD, true>(P, st, tid, lane, rem, bmw, sg * FRONT_STAGE_BYTES);
+		else exact_chunks<MASKED, FOLD, false>(P, st, tid, lane, rem, bmw, sg * FRONT_STAGE_BYTES);
 		__syncthreads();
 		if (tid == 0) issue((uint64_t)it + FRONT_NST);
 	}
@@ -430,6 +409,9 @@ int exact_count_launch(const agb_desc &d, Workspace &W, const void *d_text, uint
 	F.stage_begin = 0; F.stage_end = (n_words + FRONT_WORDS_PER_STAGE - 1) / FRONT_WORDS_PER_STAGE;
 	F.fold = d.anchor_fold; F.amask = d.anchor_mask; F.anchor[0] = d.anchor[0]; F.alen = d.anchor_len;
 	F.delim4 = d.delim[0] * 0x01010101u;
+	/* the scaled differences of exact_chunks (run-time values keep the multiplies on the FMA pipe) */
+	F.scale = 1u << (8 * (4 - d.anchor_len)); F.coef[0] = d.anchor[0] * F.scale;
+	F.coef3[0] = 2u; F.coef3[1] = (uint32_t)d.delim[0] << 24; F.coef3[2] = 1u << 24;
 	const unsigned grid = (unsigned)std::min<uint64_t>(F.stage_end, (uint64_t)W.sm_count * FRONT_CTAS_PER_SM);
 	const bool masked = d.anchor_mask != 0xFFFFFFFFu, fold = d.anchor_fold != 0;
 	static bool configured[64][4] = {{false}};

@@ -66,8 +66,8 @@ std::mutex g_ws_mu[64];          /* one scan at a time per DEVICE (its workspace
 static int ws_prepare(Workspace &W, uint64_t n)
 {
 	if (!W.totals) {
-		CUDA_TRY(cudaMalloc(&W.totals, 16 * sizeof(unsigned long long)));
-		CUDA_TRY(cudaMallocHost(&W.h_totals, 16 * sizeof(unsigned long long)));
+		CUDA_TRY(cudaMalloc(&W.totals, 24 * sizeof(unsigned long long)));
+		CUDA_TRY(cudaMallocHost(&W.h_totals, 24 * sizeof(unsigned long long)));
 		CUDA_TRY(cudaMalloc(&W.d_desc, sizeof(agb_desc)));
 		CUDA_TRY(cudaMalloc(&W.range_counts, REFINE_MAX_RANGES * sizeof(uint32_t)));
 		CUDA_TRY(cudaMalloc(&W.range_offsets, REFINE_MAX_RANGES * sizeof(uint64_t)));
@@ -233,7 +233,7 @@ static bool refine_cannot_thin(const agb_desc &d) { return d.k == 0 && d.n_ancho
 
 static int fetch_result(Workspace &W, int want, uint64_t capacity, bool refined, cudaStream_t st, agb_result *res)
 {
-	CUDA_TRY(cudaMemcpyAsync(W.h_totals, W.totals, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaMemcpyAsync(W.h_totals, W.totals, 24 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));   /* [16..18]: shard_aux_enqueue */
 	CUDA_TRY(cudaStreamSynchronize(st));
 	res->n_matched = W.h_totals[0];
 	res->n_flagged = refined ? W.h_totals[12] : W.h_totals[1];
@@ -383,6 +383,9 @@ static int adaptive_plan(const agb_desc &d, Workspace &W, const void *d_text, ui
  * host synchronisation of a scan).  The candidate list of the list form is sized without asking the device how many
  * survivors there are; should it turn out too small (totals[12] > capacity, seen in the read-back) the record stage
  * alone is run again with the right size -- or in its every-byte form when the survivors are dense. */
+/* shard.cu: the delimiter counts of the halos and the run check of the left halo, into totals[16..18] (read back with the rest) */
+int shard_aux_enqueue(const agb_desc &d, Workspace &W, const uint8_t *text, const ShardInfo *sh, bool ordinals, cudaStream_t st);
+
 static int stages_after_front(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, bool use_front, bool count_in_front,
                               int want, int want_level, agb_record *d_records, uint64_t capacity, cudaStream_t st, agb_result *res,
                               const ShardInfo *sh = nullptr)
@@ -396,6 +399,7 @@ static int stages_after_front(const agb_desc &d, Workspace &W, const void *d_tex
 		rc = records_launch(d, W, d_text, n, use_front, refined, want, want_level, d_records, capacity, st, sh); if (rc) return rc;
 		if (want & AGB_WANT_ORDINALS) { rc = ordinals_launch(d, W, d_text, n, (want & AGB_WANT_RECORDS) ? d_records : nullptr, capacity, st, count_in_front); if (rc) return rc; }
 		CUDA_TRY(cudaEventRecord(W.e2, st));
+		if (sh) { rc = shard_aux_enqueue(d, W, (const uint8_t *)d_text, sh, (want & AGB_WANT_ORDINALS) != 0, st); if (rc) return rc; }
 		rc = fetch_result(W, want, capacity, use_front && refined, st, res); if (rc) return rc;
 		if (!(use_front && refined)) break;
 		const uint64_t ncand = W.h_totals[12];

@@ -202,6 +202,17 @@ __global__ void __launch_bounds__(256) k_gather_compact(const agb_record *pad, a
 	}
 }
 
+int shard_aux_enqueue(const agb_desc &d, Workspace &W, const uint8_t *text, const ShardInfo *sh, bool ordinals, cudaStream_t st)
+{
+	const bool first = sh->own_lo == INT64_MIN, open_end = sh->own_hi == INT64_MAX;
+	k_shard_aux<<<1, 32, 0, st>>>(text, ordinals ? W.ord_blocks : nullptr, W.tile_offsets, first ? 0 : (uint64_t)sh->own_lo,
+	                              open_end ? 0 : (uint64_t)sh->own_hi, open_end ? 0 : 1,
+	                              d.delim_kind, d.delim[0] | d.delim_fold[0], d.delim_fold[0], W.totals + 16);
+	g_launches++;
+	CUDA_TRY(cudaGetLastError());
+	return AGB_OK;
+}
+
 static int comm_buffers(agb_comm *c, uint64_t local_cap, uint64_t pad_cap)
 {
 	if (local_cap > c->local_cap) {
@@ -236,22 +247,16 @@ static int shard_scan_geom(const agb_desc &d, const void *d_shard, uint64_t n_lo
 	if (rc) return rc;
 	memset(part, 0, sizeof *part);
 	int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
-	/* the delimiter counts of the halos (ordinals) and the run check of the left halo */
+	/* the delimiter counts of the halos (ordinals) and the run check of the left halo came back with the scan's result
+	 * (shard_aux_enqueue, launched by the scan before its one read-back) */
 	std::lock_guard<std::mutex> lk(g_ws_mu[dev]);
 	Workspace &W = g_ws[dev];
 	const bool ord = (want & AGB_WANT_ORDINALS) != 0;
-	const uint64_t x_lo = first ? 0 : halo_left, x_hi = halo_left + n_local;
-	k_shard_aux<<<1, 32, 0, st>>>(text, ord ? W.ord_blocks : nullptr, W.tile_offsets, x_lo, x_hi, open_end ? 0 : 1,
-	                              d.delim_kind, d.delim[0] | d.delim_fold[0], d.delim_fold[0], W.totals + 8);
-	g_launches++;
-	CUDA_TRY(cudaGetLastError());
-	CUDA_TRY(cudaMemcpyAsync(W.h_totals + 8, W.totals + 8, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-	CUDA_TRY(cudaStreamSynchronize(st));
-	if (W.h_totals[10]) { snprintf(g_err, sizeof g_err, "a run of the delimiter longer than the left halo (%llu bytes) crosses the start of this shard", (unsigned long long)halo_left); return AGB_ERR_ARG; }
+	if (W.h_totals[18]) { snprintf(g_err, sizeof g_err, "a run of the delimiter longer than the left halo (%llu bytes) crosses the start of this shard", (unsigned long long)halo_left); return AGB_ERR_ARG; }
 	part->byte_base = -(int64_t)halo_left;
 	if (ord) {
 		const unsigned long long total = lres->n_closes - (unsigned long long)W.ord_virt;     /* delimiter ends the local scan saw */
-		const unsigned long long s_lo = W.h_totals[8], s_hi = open_end ? total : W.h_totals[9];
+		const unsigned long long s_lo = W.h_totals[16], s_hi = open_end ? total : W.h_totals[17];
 		part->closes = s_hi - s_lo;
 		/* local ordinals count the local virtual '\n' and j0 correction, and the ends of the left halo */
 		part->ord_fix = (long long)W.ord_virt + W.ord_j0 + (long long)s_lo;
