@@ -93,14 +93,42 @@ def all_core_reference(ag, cores, shard_mib, steps=2):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md's clocks line): NVML polled every 2 ms from a
+    thread of this process (the timed region of a sharded run is a few tens of milliseconds, shorter than `nvidia-smi`
+    takes to start), `nvidia-smi -lms` as the fallback; only the samples between begin() and end() count."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
-    def __init__(self, gpu_index):
-        self.idx, self.proc, self.lines = gpu_index, None, []
+    def __init__(self, gpu_index, uuid=None):
+        self.idx, self.uuid, self.proc, self.lines = gpu_index, uuid, None, []
+        self.samples, self.stop_flag, self.t0, self.t1, self.nvml, self.mx = [], False, None, None, None, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(self.uuid if isinstance(self.uuid, bytes) else str(self.uuid).encode())
+                except Exception:
+                    h = None
+            if h is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = self.idx
+                if vis:
+                    ent = vis.split(",")[self.idx].strip()
+                    phys = int(ent) if ent.isdigit() else None
+                h = pynvml.nvmlDeviceGetHandleByIndex(phys) if phys is not None else pynvml.nvmlDeviceGetHandleByUUID(ent.encode())
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.nvml = (pynvml, h, reasons)
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -110,13 +138,37 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        pynvml, h, reasons = self.nvml
+        while not self.stop_flag:
+            try:
+                self.samples.append((time.perf_counter(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), int(reasons(h))))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _pump(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln)
+            self.lines.append((time.perf_counter(), ln))
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            inside = [x for x in self.samples if self.t0 is None or (self.t0 <= x[0] <= (self.t1 or x[0]))]
+            mask = 0
+            for x in inside:
+                mask |= x[2]
+            return {"sm_mhz": statistics.median([x[1] for x in inside]) if inside else None, "sm_max_mhz": self.mx,
+                    "reasons": sorted(name for bit, name in self.REASONS if mask & bit), "samples": len(inside), "source": "nvml, 2 ms period"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         try:
@@ -124,7 +176,7 @@ class ClockSampler:
         except Exception:
             pass
         sm, mx, reasons = [], None, set()
-        for ln in self.lines:
+        for ts, ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -136,7 +188,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -419,7 +471,11 @@ def main():
     for _ in range(args.warmup):
         res, gathered = step()
     launches0 = L.agb_kernel_launches()
-    sampler = ClockSampler(local)
+    try:
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local, uuid)
     if rank == 0:
         sampler.start()
     if dist:
@@ -427,12 +483,14 @@ def main():
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     front_ms, rec_ms = [], []
+    sampler.begin()
     e0.record()
     for _ in range(args.steps):
         res, gathered = step()
         front_ms.append(res.ms_front); rec_ms.append(res.ms_records)
     e1.record()
     torch.cuda.synchronize()
+    sampler.end()
     if dist:
         dist.barrier()
     ms_total = e0.elapsed_time(e1)
