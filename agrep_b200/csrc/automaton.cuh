@@ -81,17 +81,46 @@ struct WindowReader {
 	}
 };
 
+/* does the delimiter occur with its last byte at q (file offset)? */
+template <typename RD>
+__device__ __forceinline__ bool delim_occurs(RD &R, int64_t q, const uint8_t *delim, const uint8_t *dfold, int L)
+{
+	for (int t = 0; t < L; t++) if ((R.get(q - t) | dfold[L - 1 - t]) != delim[L - 1 - t]) return false;
+	return true;
+}
+
+/* kind 2 -- a delimiter that overlaps itself and is not a run ("aba", "=-="): the automaton takes occurrences from the
+ * left and drops those that share a byte with one it took (after a close the state keeps no delimiter position:
+ * asearch.c:55-57, 175-186).  Occurrences that share bytes form a chain, and what is taken in a chain depends only on
+ * where the chain starts: walk back to its first occurrence, then forward. */
+template <typename RD>
+__device__ __noinline__ int64_t delim_chain_first(RD &R, int64_t q, const uint8_t *delim, const uint8_t *dfold, int L)
+{
+	int64_t e = q;
+	for (;;) {
+		int64_t found = e;
+		for (int64_t c = e - L + 1; c < e; c++) if (delim_occurs(R, c, delim, dfold, L)) { found = c; break; }
+		if (found == e) return e;
+		e = found;
+	}
+}
+template <typename RD>
+__device__ __noinline__ bool delim_chain_takes(RD &R, int64_t q, const uint8_t *delim, const uint8_t *dfold, int L)
+{
+	int64_t last = delim_chain_first(R, q, delim, dfold, L);
+	for (int64_t e = last + 1; e <= q; e++) if (e - L + 1 > last && delim_occurs(R, e, delim, dfold, L)) last = e;
+	return last == q;
+}
+
 /* is q (file offset, < n) the last byte of a delimiter that closes a record?  kind 0: every occurrence
  * does (no self overlap); kind 1 (c^L, e.g. $$): greedy, non-overlapping from the start of the run of c,
- * the virtual '\n' counting as part of the run (asearch.c:55-57 D_Mask + the reset at :181). */
+ * the virtual '\n' counting as part of the run (asearch.c:55-57 D_Mask + the reset at :181); kind 2: above. */
 template <typename RD>
 __device__ __forceinline__ bool delim_ends_at(RD &R, int64_t q, const uint8_t *delim, const uint8_t *dfold, int L, int kind)
 {
 	if (L == 1) return (R.get(q) | dfold[0]) == delim[0];
-	if (kind == 0) {
-		for (int t = 0; t < L; t++) if ((R.get(q - t) | dfold[L - 1 - t]) != delim[L - 1 - t]) return false;
-		return true;
-	}
+	if (kind == 0) return delim_occurs(R, q, delim, dfold, L);
+	if (kind == 2) return delim_occurs(R, q, delim, dfold, L) && delim_chain_takes(R, q, delim, dfold, L);
 	const int c = delim[0], f = dfold[0];
 	if ((R.get(q) | f) != c) return false;
 	int64_t len = 1, p = q - 1;

@@ -266,6 +266,13 @@ __device__ __forceinline__ uint32_t ord_count_seq(Reader &R, const OrdParams &P,
 		}
 		return cnt;
 	}
+	if (P.kind == 2) {
+		/* the occurrence taken last before `from` that can still shadow one ending at or after it, then greedily on */
+		int64_t last = -(1ll << 60);
+		for (int64_t e = from - 1; e > from - P.L; e--) if (delim_ends_at(R, e, P.delim, P.dfold, P.L, 2)) { last = e; break; }
+		for (int64_t q = from; q < to; q++) if (q - P.L + 1 > last && delim_occurs(R, q, P.delim, P.dfold, P.L)) { cnt++; last = q; }
+		return cnt;
+	}
 	const int c = P.delim[0], f = P.dfold[0];
 	int64_t run = 0;
 	for (int64_t q = from - 1; q >= -1 && (R.get(q) | f) == c; q--) run++;       /* (-1 is the virtual '\n') */

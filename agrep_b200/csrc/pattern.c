@@ -322,9 +322,7 @@ int agbi_derive(agb_desc *d, char *err, size_t errlen)
 	if (L == 1 || !has_border(fd, L)) d->delim_kind = 0;
 	else {
 		for (p = 1; p < L; p++) if (fd[p] != fd[0]) break;
-		if (p < L) FAIL("delimiter '%.*s' overlaps itself in a way the device record search does not support "
-		                "(supported: any 1-byte delimiter, self-overlap-free delimiters, and runs such as $$)", L, d->delim);
-		d->delim_kind = 1;
+		d->delim_kind = p < L ? 2 : 1;          /* a run such as $$, or any other self-overlap ("aba"): automaton.cuh delim_ends_at */
 	}
 	reset_rows(d, d->mask[d->delim[L - 1]], d->reset);
 	/* the virtual '\n' in front of the text (bitap.c:140,148-149) */
@@ -562,7 +560,7 @@ const agb_desc *agb_pattern_desc(const agb_pattern *p) { return p ? &p->d : NULL
 void agb_fill_ordinals(const agb_pattern *p, const void *h_text, uint64_t n, agb_record *records, uint64_t n_records)
 {
 	const agb_desc *d = &p->d; const unsigned char *t = (const unsigned char *)h_text;
-	const int L = d->L; uint64_t i = 0; long long j = 0, run = 0, q; unsigned char fd[2 * AGB_MAXDELIM + 2]; int z, head = 1;
+	const int L = d->L; uint64_t i = 0; long long j = 0, run = 0, q, taken = -(1ll << 60); unsigned char fd[2 * AGB_MAXDELIM + 2]; int z, head = 1;
 	if (!n_records) return;
 	folded_delim(d, fd);
 #define DEQ(c, p) ((((c) | d->delim_fold[p]) & 0x1FF) == fd[p])
@@ -574,6 +572,16 @@ void agb_fill_ordinals(const agb_pattern *p, const void *h_text, uint64_t n, agb
 		int c = q < 0 ? '\n' : (q < (long long)n ? t[q] : d->delim[q - (long long)n]), e;
 		if (L == 1) e = DEQ(c, 0);
 		else if (d->delim_kind == 1) { run = DEQ(c, 0) ? run + 1 : 0; e = run > 0 && run % L == 0; }
+		else if (d->delim_kind == 2) {
+			/* occurrences are taken from the left; one that shares a byte with the one taken before it is dropped */
+			int m = 1, u;
+			for (u = 0; u < L && m; u++) {
+				long long at = q - u; int cc = at < -1 ? 256 : (at < 0 ? '\n' : (at < (long long)n ? t[at] : d->delim[at - (long long)n]));
+				if (!DEQ(cc, L - 1 - u)) m = 0;
+			}
+			e = m && q - L + 1 > taken;
+			if (e) taken = q;
+		}
 		else {
 			int m = 1, u;
 			for (u = 0; u < L && m; u++) {

@@ -384,7 +384,7 @@ static int adaptive_plan(const agb_desc &d, Workspace &W, const void *d_text, ui
  * survivors there are; should it turn out too small (totals[12] > capacity, seen in the read-back) the record stage
  * alone is run again with the right size -- or in its every-byte form when the survivors are dense. */
 /* shard.cu: the delimiter counts of the halos and the run check of the left halo, into totals[16..18] (read back with the rest) */
-int shard_aux_enqueue(const agb_desc &d, Workspace &W, const uint8_t *text, const ShardInfo *sh, bool ordinals, cudaStream_t st);
+int shard_aux_enqueue(const agb_desc &d, Workspace &W, const uint8_t *text, uint64_t n, const ShardInfo *sh, bool ordinals, cudaStream_t st);
 
 static int stages_after_front(const agb_desc &d, Workspace &W, const void *d_text, uint64_t n, bool use_front, bool count_in_front,
                               int want, int want_level, agb_record *d_records, uint64_t capacity, cudaStream_t st, agb_result *res,
@@ -399,7 +399,7 @@ static int stages_after_front(const agb_desc &d, Workspace &W, const void *d_tex
 		rc = records_launch(d, W, d_text, n, use_front, refined, want, want_level, d_records, capacity, st, sh); if (rc) return rc;
 		if (want & AGB_WANT_ORDINALS) { rc = ordinals_launch(d, W, d_text, n, (want & AGB_WANT_RECORDS) ? d_records : nullptr, capacity, st, count_in_front); if (rc) return rc; }
 		CUDA_TRY(cudaEventRecord(W.e2, st));
-		if (sh) { rc = shard_aux_enqueue(d, W, (const uint8_t *)d_text, sh, (want & AGB_WANT_ORDINALS) != 0, st); if (rc) return rc; }
+		if (sh) { rc = shard_aux_enqueue(d, W, (const uint8_t *)d_text, n, sh, (want & AGB_WANT_ORDINALS) != 0, st); if (rc) return rc; }
 		rc = fetch_result(W, want, capacity, use_front && refined, st, res); if (rc) return rc;
 		if (!(use_front && refined)) break;
 		const uint64_t ncand = W.h_totals[12];

@@ -14,6 +14,7 @@
  *     the gathered headers.
  */
 #include "scan_internal.cuh"
+#include "automaton.cuh"
 #include <nccl.h>
 #include <dlfcn.h>
 
@@ -159,7 +160,9 @@ extern "C" int agb_shard_halo(agb_comm *c, void *d_shard, uint64_t n_local, void
 
 /* delimiter ends in [0, x) of the local scan, x a multiple of 512, from the block and tile counts the ordinals pass
  * left behind; and the check that a run delimiter ("$$") that reaches the cut begins inside the left halo */
-__global__ void k_shard_aux(const uint8_t *text, const uint16_t *blocks, const uint64_t *tile_off, uint64_t x_lo, uint64_t x_hi, int have_hi,
+struct RawReader { const uint8_t *t; uint64_t n; __device__ __forceinline__ int get(int64_t p) { return (p < 0 || (uint64_t)p >= n) ? 256 : t[p]; } };
+
+__global__ void k_shard_aux(const uint8_t *text, uint64_t n, const agb_desc *D, const uint16_t *blocks, const uint64_t *tile_off, uint64_t x_lo, uint64_t x_hi, int have_hi,
                             int kind, int delim0, int dfold0, unsigned long long *out /* [0] S(x_lo), [1] S(x_hi), [2] run error */)
 {
 	if (threadIdx.x || blockIdx.x) return;
@@ -178,6 +181,15 @@ __global__ void k_shard_aux(const uint8_t *text, const uint16_t *blocks, const u
 		int64_t p = (int64_t)x_lo - 1;
 		while (p >= 0 && (text[p] | dfold0) == delim0) p--;
 		if (p < 0) bad = 1;                                 /* the run covers the whole left halo: where it began is unknown */
+	}
+	if (kind == 2 && x_lo > 0) {
+		/* a chain of overlapping occurrences that crosses the cut must begin inside the left halo, clear of its first bytes */
+		RawReader R; R.t = text; R.n = n;
+		const int L = D->L;
+		uint8_t dl[2 * AGB_MAXDELIM + 2], df[2 * AGB_MAXDELIM + 2];
+		for (int i = 0; i < L; i++) { df[i] = D->delim_fold[i]; dl[i] = D->delim[i] | df[i]; }
+		for (int64_t e = (int64_t)x_lo; e <= (int64_t)x_lo + L - 2; e++)
+			if (delim_occurs(R, e, dl, df, L) && delim_chain_first(R, e, dl, df, L) - L + 1 < L) bad = 1;
 	}
 	out[2] = bad;
 }
@@ -202,10 +214,10 @@ __global__ void __launch_bounds__(256) k_gather_compact(const agb_record *pad, a
 	}
 }
 
-int shard_aux_enqueue(const agb_desc &d, Workspace &W, const uint8_t *text, const ShardInfo *sh, bool ordinals, cudaStream_t st)
+int shard_aux_enqueue(const agb_desc &d, Workspace &W, const uint8_t *text, uint64_t n, const ShardInfo *sh, bool ordinals, cudaStream_t st)
 {
 	const bool first = sh->own_lo == INT64_MIN, open_end = sh->own_hi == INT64_MAX;
-	k_shard_aux<<<1, 32, 0, st>>>(text, ordinals ? W.ord_blocks : nullptr, W.tile_offsets, first ? 0 : (uint64_t)sh->own_lo,
+	k_shard_aux<<<1, 32, 0, st>>>(text, n, W.d_desc, ordinals ? W.ord_blocks : nullptr, W.tile_offsets, first ? 0 : (uint64_t)sh->own_lo,
 	                              open_end ? 0 : (uint64_t)sh->own_hi, open_end ? 0 : 1,
 	                              d.delim_kind, d.delim[0] | d.delim_fold[0], d.delim_fold[0], W.totals + 16);
 	g_launches++;

@@ -23,7 +23,24 @@ def _delim_ends_at(text, q, delim):
     L = len(delim)
     if L == 1:
         return text[q] == delim[0]
-    if any(delim[:b] == delim[L - b:] for b in range(1, L)):          # self-overlapping: only runs c^L are supported
+    if any(delim[:b] == delim[L - b:] for b in range(1, L)) and len(set(delim)) > 1:
+        # overlaps itself and is not a run ("aba"): occurrences are taken from the left, one that shares a byte with the one
+        # taken before it is dropped; what a chain of overlapping occurrences yields depends on where it starts
+        occ = lambda e: e + 1 >= L and bytes(text[e + 1 - L:e + 1]) == bytes(delim)
+        if not occ(q):
+            return False
+        e = q
+        while True:
+            prev = next((c for c in range(e - L + 1, e) if occ(c)), None)
+            if prev is None:
+                break
+            e = prev
+        last = e
+        for c in range(e + 1, q + 1):
+            if c - L + 1 > last and occ(c):
+                last = c
+        return last == q
+    if any(delim[:b] == delim[L - b:] for b in range(1, L)):          # a run c^L: pairs from the start of the run
         c = delim[0]
         if text[q] != c:
             return False

@@ -46,3 +46,20 @@ def mutate(rnd, s, nedits):
         else:
             s.insert(p, rnd.choice("abcdefghijklmnopqrstuvwxyz"))
     return "".join(s)
+
+
+def overlap_text(delim, seed=3):
+    """records separated by a delimiter that overlaps itself, with chains of overlapping occurrences between some of them
+    ("ababa", "abababa", "abaaba" for "aba"): no digits or colons, so that -n prefixes can be found in the output"""
+    import random
+    rnd = random.Random(seed)
+    words = [w for w in make_text(300, seed=seed).decode().split() if w.isalpha()]
+    d = delim
+    per = next(p for p in range(1, len(d) + 1) if d[p:] == d[:len(d) - p])       # the delimiter's period
+    out = []
+    for i in range(400):
+        out.append(" ".join(rnd.choice(words) for _ in range(rnd.randint(0, 6))))
+        r = rnd.random()
+        chain = d if r < 0.5 else d + d[len(d) - per:] * rnd.randint(1, 4) if r < 0.8 else d + d if r < 0.9 else d[:per] + d
+        out.append(chain)
+    return "".join(out).encode()

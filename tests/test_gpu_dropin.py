@@ -11,6 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "oracle", "_ref", "agrep")
 DROP = os.path.join(ROOT, "oracle", "_ref", "agrep_dropin")
 
+from _corpus import overlap_text
+
 
 @pytest.fixture(scope="module")
 def files():
@@ -22,7 +24,8 @@ def files():
                        ("para.txt", _corpus.make_text(2500, seed=13, paragraphs=True)),
                        ("small.txt", _corpus.make_text(600, seed=14)),       # < 48 KiB: no block artefacts in -b
                        ("semi.txt", _corpus.make_text(300, seed=15).replace(b"\n", b";").replace(b"the", b"Hello", 30).replace(b"and", b"xhello", 10) + b"last hello there"),   # (not "hello" at the very end: bm()'s sentinel copy of the pattern behind the text makes -w see a letter there)
-                       ("blank.txt", b"\n" * 3000 + b"one the two\n" + b"\n" * 3000 + b"x\n\n\ny")):   # more than half of the bytes close a record
+                       ("blank.txt", b"\n" * 3000 + b"one the two\n" + b"\n" * 3000 + b"x\n\n\ny"),   # more than half of the bytes close a record
+                       ("aba.txt", overlap_text("aba", 5))):      # a delimiter that overlaps itself, with chains ("abababa")
 
         paths[name] = os.path.join(d, name)
         open(paths[name], "wb").write(data)
@@ -68,6 +71,8 @@ CASES = [
     (["-c", "-w", "-d", ";", "hello"], ["semi.txt"]),
     (["-n", "-v", "zzz"], ["blank.txt"]),                        # every blank line is a reported record (list longer than n/2)
     (["-c", "-n", "^$"], ["blank.txt"]),
+    (["-n", "-d", "aba", "-1", "state"], ["aba.txt"]),           # occurrences taken from the left, overlapping ones dropped
+    (["-c", "-n", "-d", "aba", "e"], ["aba.txt"]),
     (["-n", "-1", "^$"], ["blank.txt"]),
 ]
 

@@ -174,7 +174,7 @@ def test_random_metachar_differential():
         if rnd.random() < 0.8: kw["linenum"] = 1
         for p_, key in ((0.25, "nocase"), (0.15, "wordbound"), (0.1, "inverse"), (0.05, "ins_free"), (0.04, "wholeline")):
             if rnd.random() < p_: kw[key] = 1
-        if rnd.random() < 0.15: kw["delim"] = rnd.choice(["$$", "e ", "ab", "\\."])
+        if rnd.random() < 0.15: kw["delim"] = rnd.choice(["$$", "e ", "ab", "\\.", "e e", "ee "])
         if kw["k"] and rnd.random() < 0.06: kw["cost_s"] = 2
         try:
             a = _oracle.compile(pat, **kw)
@@ -183,7 +183,7 @@ def test_random_metachar_differential():
         try:
             p = ag.Pattern(pat, **api_kw(kw))
         except ag.AgrepError as e:
-            assert "delimiter" in str(e), (pat, kw, e)          # the two documented refusals
+            assert "delimiter" in str(e) and kw.get("ins_free"), (pat, kw, e)     # the documented refusal: -p with a multi-byte delimiter
             continue
         cnt, recs = _oracle.scan(a, data)
         res, got = p.scan_host(data, ordinals=True)
@@ -367,3 +367,23 @@ def test_case_insensitive_delimiters(delim):
             res, got = ag.Pattern(pat, **kw).scan_host(d, ordinals=True)
             assert res.n_matched == cnt and cnt > 0, (pat, delim)
             assert [t[:3] for t in got] == list(recs), (pat, delim)
+
+
+@pytest.mark.parametrize("delim", ["aba", "abab", "=-=", "e e", "xyx"])
+def test_self_overlapping_delimiters(delim):
+    """delimiters that overlap themselves and are not runs (delim_kind 2): occurrences are taken from the left, one that shares
+    a byte with the one taken before it is dropped; the record stages find record starts by walking the chain of overlapping
+    occurrences back to its first.  List with ordinals and count against the oracle, in the list form (anchors), the tile
+    form (classes, -v) and with errors."""
+    from _corpus import overlap_text
+    for seed in (3, 4, 5):
+        data = overlap_text(delim, seed)
+        for d in (data, delim.encode() + data, data + delim.encode(), data[:-len(delim)] + delim.encode()[:-1]):
+            for pat, kw in (("state", dict(k=1, linenum=1)), ("e", dict(k=0, linenum=1)), ("world", dict(k=0, linenum=1, inverse=1)),
+                            ("[st]tat.", dict(k=0, linenum=1)), ("because", dict(k=2, linenum=1, nocase=1))):
+                a = _oracle.compile(pat, delim=delim, **kw)
+                cnt, recs = _oracle.scan(a, d)
+                p = ag.Pattern(pat, delim=delim, **api_kw(kw))
+                res, got = p.scan_host(d, ordinals=True)
+                assert res.n_matched == cnt and [t[:3] for t in got] == [t[:3] for t in recs], (delim, pat, seed)
+                assert p.scan_host(d, want_records=False)[0].n_matched == cnt

@@ -79,12 +79,15 @@ def test_shards_of_newline_records(world, pattern, kw):
 
 @pytest.mark.parametrize("world", [2, 4])
 @pytest.mark.parametrize("delim,dbytes,kw", [("$$", b"\n\n", dict(k=1, linenum=1, wordbound=1)), ("; ", b"; ", dict(k=1, linenum=1)),
-                                             ("$$", b"\n\n", dict(k=0, linenum=1, inverse=1))])
+                                             ("$$", b"\n\n", dict(k=0, linenum=1, inverse=1)), ("aba", b"aba", dict(k=1, linenum=1))])
 def test_shards_of_user_delimiters(world, delim, dbytes, kw):
     """paragraph records (runs of newlines that straddle the cuts: the left halo resolves the greedy pairing) and a
     2-byte delimiter whose bytes fall on either side of a cut"""
     if dbytes == b"\n\n":
         data = _corpus.make_text(2500, seed=31, paragraphs=True) + b"\n" * 7 + _corpus.make_text(800, seed=32, paragraphs=True)
+    elif dbytes == b"aba":
+        from _corpus import overlap_text      # chains of overlapping occurrences ("abababa") across the cuts
+        data = overlap_text("aba", 7) + overlap_text("aba", 8)
     else:
         data = ragged_text(6, sep="; ")
     for shift in (0, 1, 3):                                  # move the text under the fixed cuts

@@ -223,3 +223,26 @@ def test_random_metachar_differential(ref_agrep):
         assert [r[2] - 1 for r in recs] == [int(m.group(1)) for m in re.finditer(rb"^(\d+): ", p.stdout, re.M)], (pat, args)
         compared += 1
     assert compared > 100
+
+
+from _corpus import overlap_text
+
+
+@pytest.mark.parametrize("delim", ["aba", "abab", "=-=", "e e", "xyx"])
+@pytest.mark.parametrize("pattern,kw,rargs", [("state", dict(k=1, linenum=1), ["-1"]), ("e", dict(k=0, linenum=1), []),
+                                              ("world", dict(k=0, linenum=1, inverse=1), ["-v"])])
+def test_self_overlapping_delimiters(ref_agrep, delim, pattern, kw, rargs):
+    """a delimiter that overlaps itself: the automaton takes occurrences from the left and drops those that share a byte with
+    one it took (asearch.c:55-57, 175-186) -- count and ordinals of the restatement against the reference binary"""
+    if not ref_agrep:
+        pytest.skip("reference binary not built")
+    for seed in (3, 4):
+        data = overlap_text(delim, seed)
+        for d in (data, delim.encode() + data, data + delim.encode(), data[:-len(delim)] + delim.encode()[:-1]):
+            a = _oracle.compile(pattern, delim=delim, **kw)
+            cnt, recs = _oracle.scan(a, d)
+            assert cnt > 3
+            assert cnt == ref_count(ref_agrep, ["-n"] + rargs + ["-d", delim, pattern], d), (delim, pattern)
+            out = run_ref(ref_agrep, ["-n"] + rargs + ["-d", delim, pattern], d)
+            # (with a user delimiter -n prints j itself: the record count starts one lower, bitap.c:151-156 / agrep.c:3878)
+            assert [r[2] for r in recs] == [int(m.group(1)) for m in re.finditer(rb"(\d+): ", out)], (delim, pattern)
