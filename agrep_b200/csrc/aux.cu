@@ -414,7 +414,14 @@ int ordinals_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_
 	W.ord_j0 = P.j0;
 	if (blocks_counted) { k_ord_tiles<<<(unsigned)((tiles + 255) / 256), 256, 0, st>>>(P, tiles); g_launches++; }     /* stage 1 counted the blocks */
 	else { k_delim_count<<<(unsigned)tiles, ORD_THREADS, 0, st>>>(P); g_launches++; }
-	k_scan_tiles<<<1, 1024, 0, st>>>(W.tile_counts, W.tile_offsets, tiles, W.totals + 13); g_launches++;
+	const uint64_t nb = (tiles + SCAN_BLOCK - 1) / SCAN_BLOCK;
+	if (tiles > 4 * SCAN_BLOCK && nb <= W.scan_cap) {
+		/* two million tile counts at 64 GiB: one block would take 1.6 ms over them */
+		k_scan_partial<<<(unsigned)nb, 1024, 0, st>>>(W.tile_counts, tiles, W.scan_sums, nullptr);
+		k_scan_tiles<<<1, 1024, 0, st>>>(W.scan_sums, W.scan_offs, nb, W.totals + 13);
+		k_scan_apply<<<(unsigned)nb, 1024, 0, st>>>(W.tile_counts, tiles, W.scan_offs, W.tile_offsets, nullptr);
+		g_launches += 3;
+	} else { k_scan_tiles<<<1, 1024, 0, st>>>(W.tile_counts, W.tile_offsets, tiles, W.totals + 13); g_launches++; }
 	if (d_records && capacity) {
 		/* the list length is on the device (totals[0]); one thread per possible entry, bounded by the capacity */
 		CUDA_TRY(cudaMemcpyAsync(W.h_totals, W.totals, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));

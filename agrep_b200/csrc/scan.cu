@@ -477,14 +477,37 @@ static void par_memcpy(uint8_t *dst, const uint8_t *src, size_t len)
 
 /* Host text -> HBM -> scan: the replacement of the fill_buf()/read(2) loop (bitap.c:143,450-477).  The text is
  * moved in 64 MiB slices on a copy stream -- straight from the caller's memory when it is page-locked; through a
- * pinned ring filled by 4 host threads when it is pageable; read(2) straight into the pinned ring when the
- * source is a file descriptor -- while stage 1 runs on the slice that arrived before (its last chunk looks 4
+ * pinned ring filled by 4 host threads when it is pageable; pread(2) by 4 threads straight into the pinned ring when the
+ * source is a regular file -- while stage 1 runs on the slice that arrived before (its last chunk looks 4
  * bytes into the next one), so the scan hides behind PCIe; stages 1.5 and 2 run once over the whole bitmap. */
 struct SliceSource {
 	const uint8_t *mem;      /* host memory source, or NULL */
 	bool pinned;             /* mem is page-locked: copy from it directly */
-	int fd;                  /* file descriptor source when mem == NULL */
+	int fd;                  /* file descriptor source when mem == NULL (a regular file) */
+	off_t fd_off = 0;        /* where the text starts in it */
 };
+
+/* a slice of a regular file into the pinned ring: 4 host threads pread(2) a quarter each (one thread's read(2) from the page
+ * cache is a third of what PCIe takes) */
+static bool par_pread(int fd, off_t at, uint8_t *dst, size_t len)
+{
+	const int T = 4; const size_t part = ((len + T - 1) / T + 4095) & ~(size_t)4095;
+	std::thread th[T]; int used = 0; std::atomic<int> bad{0};
+	for (int t = 0; t < T; t++) {
+		size_t a = (size_t)t * part; if (a >= len) break;
+		size_t l = std::min(part, len - a);
+		th[used++] = std::thread([=, &bad] {
+			size_t got = 0;
+			while (got < l) {
+				ssize_t r = pread(fd, dst + a + got, l - got, at + (off_t)(a + got));
+				if (r <= 0) { bad = 1; return; }
+				got += (size_t)r;
+			}
+		});
+	}
+	for (int t = 0; t < used; t++) th[t].join();
+	return bad == 0;
+}
 
 static int scan_stream_impl(const agb_desc &d, uint64_t n, const SliceSource &src, int want,
                             agb_record *records, uint64_t capacity, agb_result *res)
@@ -531,12 +554,8 @@ static int scan_stream_impl(const agb_desc &d, uint64_t n, const SliceSource &sr
 			if (i >= STAGE_BUFS) CUDA_TRY(cudaEventSynchronize(W.ev_copy[sb]));     /* that staging buffer has been consumed */
 			if (src.mem) par_memcpy(W.stage[sb], src.mem + off, len);
 			else {
-				uint64_t got = 0;                                                   /* fill_buf(): read(2) until the slice is full */
-				while (got < len) {
-					ssize_t r = read(src.fd, W.stage[sb] + got, (size_t)(len - got));
-					if (r <= 0) { snprintf(g_err, sizeof g_err, "read(2) returned %zd at offset %llu of %llu", r, (unsigned long long)(off + got), (unsigned long long)n); return AGB_ERR_ARG; }
-					got += (uint64_t)r;
-				}
+				/* fill_buf(): the slice from the file */
+				if (!par_pread(src.fd, src.fd_off + (off_t)off, W.stage[sb], (size_t)len)) { snprintf(g_err, sizeof g_err, "pread(2) failed or hit the end of the file in [%llu, %llu) of %llu", (unsigned long long)off, (unsigned long long)(off + len), (unsigned long long)n); return AGB_ERR_ARG; }
 			}
 			CUDA_TRY(cudaMemcpyAsync(W.h2d_text + off, W.stage[sb], len, cudaMemcpyHostToDevice, W.s_copy));
 		}
@@ -586,8 +605,10 @@ extern "C" int agb_scan_fd(const agb_pattern *p, int fd, int want, agb_record *r
 		/* regular file: the size is known, read(2) goes straight into the pinned ring, slice by slice */
 		off_t cur = lseek(fd, 0, SEEK_CUR);
 		uint64_t n = (cur >= 0 && sb.st_size > cur) ? (uint64_t)(sb.st_size - cur) : 0;
-		SliceSource src; src.mem = nullptr; src.pinned = false; src.fd = fd;
-		return scan_stream_impl(p->d, n, src, want, records, capacity, res);
+		SliceSource src; src.mem = nullptr; src.pinned = false; src.fd = fd; src.fd_off = cur >= 0 ? cur : 0;
+		int rc = scan_stream_impl(p->d, n, src, want, records, capacity, res);
+		if (cur >= 0) lseek(fd, cur + (off_t)n, SEEK_SET);            /* as read(2) would have left it */
+		return rc;
 	}
 	/* pipes, ttys: fill_buf() semantics -- read until EOF into a growing buffer, then as host memory */
 	size_t cap = 1 << 20, len = 0; uint8_t *buf = (uint8_t *)malloc(cap);
@@ -635,12 +656,7 @@ static int text_upload(const SliceSource &src, uint64_t n, agb_text **out)
 			if (i >= STAGE_BUFS) CUDA_TRY(cudaEventSynchronize(W.ev_copy[sb]));
 			if (src.mem) par_memcpy(W.stage[sb], src.mem + off, len);
 			else {
-				uint64_t got = 0;
-				while (got < len) {
-					ssize_t r = read(src.fd, W.stage[sb] + got, (size_t)(len - got));
-					if (r <= 0) { snprintf(g_err, sizeof g_err, "read(2) returned %zd at offset %llu of %llu", r, (unsigned long long)(off + got), (unsigned long long)n); cudaStreamSynchronize(W.s_copy); cudaFree(t->d); delete t; return AGB_ERR_ARG; }
-					got += (uint64_t)r;
-				}
+				if (!par_pread(src.fd, src.fd_off + (off_t)off, W.stage[sb], (size_t)len)) { snprintf(g_err, sizeof g_err, "pread(2) failed or hit the end of the file in [%llu, %llu) of %llu", (unsigned long long)off, (unsigned long long)(off + len), (unsigned long long)n); cudaStreamSynchronize(W.s_copy); cudaFree(t->d); delete t; return AGB_ERR_ARG; }
 			}
 			CUDA_TRY(cudaMemcpyAsync(t->d + off, W.stage[sb], len, cudaMemcpyHostToDevice, W.s_copy));
 		}
@@ -670,8 +686,10 @@ extern "C" int agb_text_from_fd(int fd, agb_text **out)
 	if (fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode)) { snprintf(g_err, sizeof g_err, "agb_text_from_fd needs a regular file"); return AGB_ERR_ARG; }
 	off_t cur = lseek(fd, 0, SEEK_CUR);
 	const uint64_t n = (cur >= 0 && sb.st_size > cur) ? (uint64_t)(sb.st_size - cur) : 0;
-	SliceSource src; src.mem = nullptr; src.pinned = false; src.fd = fd;
-	return text_upload(src, n, out);
+	SliceSource src; src.mem = nullptr; src.pinned = false; src.fd = fd; src.fd_off = cur >= 0 ? cur : 0;
+	int rc = text_upload(src, n, out);
+	if (cur >= 0) lseek(fd, cur + (off_t)n, SEEK_SET);                /* as read(2) would have left it */
+	return rc;
 }
 
 extern "C" void agb_text_free(agb_text *t) { if (t) { cudaFree(t->d); delete t; } }

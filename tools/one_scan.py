@@ -11,7 +11,7 @@ kw = {}
 for a in sys.argv[3:]:
     k, v = a.split("=")
     kw[k] = v if k == "delim" else int(v)
-reps, want_list, para = kw.pop("reps", 3), kw.pop("list", 0), kw.pop("para", 0)
+reps, want_list, para, ordinals = kw.pop("reps", 3), kw.pop("list", 0), kw.pop("para", 0), kw.pop("ordinals", 0)
 n = int(gib * (1 << 30)) // 4096 * 4096
 t = torch.empty(n + 4096, dtype=torch.uint8, device="cuda")
 t[n:].zero_()
@@ -21,5 +21,5 @@ p = ag.Pattern(pat, **kw)
 cap = 1 << 22
 rec = torch.empty((cap, 4), dtype=torch.int64, device="cuda") if want_list else None
 for _ in range(reps):
-    r = p.scan_device(t.data_ptr(), n, d_records=rec.data_ptr() if want_list else 0, capacity=cap if want_list else 0)
+    r = p.scan_device(t.data_ptr(), n, d_records=rec.data_ptr() if want_list else 0, capacity=cap if want_list else 0, ordinals=bool(ordinals))
     print("front %.3f ms  rest %.3f ms  %.1f GB/s  matched %d flagged %d" % (r.ms_front, r.ms_records, n / (r.ms_front + r.ms_records) / 1e6, r.n_matched, r.n_flagged))
