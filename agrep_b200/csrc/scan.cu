@@ -75,7 +75,7 @@ static int ws_prepare(Workspace &W, uint64_t n)
 		int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
 		CUDA_TRY(cudaDeviceGetAttribute(&W.sm_count, cudaDevAttrMultiProcessorCount, dev));
 	}
-	uint64_t n_chunks = (n + 15) / 16, n_words = (n_chunks + 31) / 32, tiles = (n + DENSE_TILE - 1) / DENSE_TILE + 1;
+	uint64_t n_chunks = (n + 15) / 16, n_words = (n_chunks + 31) / 32, tiles = (n + std::min<uint64_t>(DENSE_TILE, SL_TILE) - 1) / std::min<uint64_t>(DENSE_TILE, SL_TILE) + 1;
 	size_t bb = (size_t)(n_words + FRONT_WORDS_PER_STAGE) * 4;
 	if (bb > W.bitmap_bytes) {
 		if (W.bitmap) cudaFree(W.bitmap);

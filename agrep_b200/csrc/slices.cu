@@ -51,7 +51,7 @@ k_records_slices(const RecParams P)
 #pragma unroll
 		for (int b = 0; b < SL_BATCH; b++) if (ok[b]) {
 			const uint32_t x = (u0 + b * SL_THREADS) * 16 + (SL_PER - SL_APRON);      /* byte number counted from the start of strip 0 */
-			uint32_t *dst = reinterpret_cast<uint32_t *>(s_text + (x >> 8) * SL_STRIDE + (x & (SL_PER - 1)));
+			uint32_t *dst = reinterpret_cast<uint32_t *>(s_text + (x / SL_PER) * SL_STRIDE + (x & (SL_PER - 1)));
 			dst[0] = v[b].x; dst[1] = v[b].y; dst[2] = v[b].z; dst[3] = v[b].w;
 		}
 	}
@@ -60,7 +60,7 @@ k_records_slices(const RecParams P)
 		const int64_t g = n + tid;
 		if (g >= tile0 - SL_APRON && g < tile_end) {
 			const uint32_t x = (uint32_t)(g - tile0 + SL_PER);
-			s_text[(x >> 8) * SL_STRIDE + (x & (SL_PER - 1))] = SH.delim[tid];
+			s_text[(x / SL_PER) * SL_STRIDE + (x & (SL_PER - 1))] = SH.delim[tid];
 		}
 	}
 	__syncthreads();
