@@ -336,18 +336,54 @@ int agbi_derive(agb_desc *d, char *err, size_t errlen)
 
 /* pigeonhole anchor plan: k errors can damage at most k of k+1 disjoint runs of consecutive literal
  * positions, so a matching record contains one run verbatim (the idea of sgrep.c:1053-1154, made exact). */
-static int collect_runs(const build_t *b, int part, int A, int ascii_only, uint32_t *out, int *where, int cap)
+/* the bytes a position accepts, when they are at most two (a literal, or a class such as [ea]); 0: not usable in an anchor */
+static int pos_values(const pos_t *q, int ascii_only, int literal_only, int *vals)
+{
+	int c, n = 0;
+	if (q->is_sep || (literal_only && q->lit < 0)) return 0;
+	if (q->lit >= 0) {
+		/* ascii_only (-i): the exact engine folds bytes >= 0x80 through the ISO-8859-1 LUT (bitap.c:171), which the
+		 * anchors' plain 0x20 fold cannot express -- such bytes never sit inside an anchor */
+		if (q->lit == '\n' || (ascii_only && q->lit >= 0x80)) return 0;
+		vals[0] = q->lit; return 1;
+	}
+	for (c = 0; c < 256; c++) if ((q->cls[c >> 6] >> (c & 63)) & 1) {
+		/* (under -i the class holds both cases and the anchors are compared with 0x20 OR-ed in: one value per letter) */
+		const int v = (ascii_only && is_alpha(c)) ? (c | 0x20) : c;
+		if (c == '\n' || (ascii_only && c >= 0x80)) return 0;
+		if (n && (vals[0] == v || (n == 2 && vals[1] == v))) continue;
+		if (n == 2) return 0;
+		vals[n++] = v;
+	}
+	return n;
+}
+
+#define PIECE_VARIANTS 4
+typedef struct { int where, nvar; uint32_t v[PIECE_VARIANTS]; } piece_t;
+
+/* disjoint runs of A consecutive positions that each accept one byte -- or two, as long as a run spells at most
+ * PIECE_VARIANTS strings: "b[ea]c" is the two anchors "bec" and "bac" at the same place */
+static int collect_runs(const build_t *b, int part, int A, int ascii_only, int literal_only, piece_t *out, int cap)
 {
 	int p, run = 0, n = 0;
 	for (p = 1; p <= b->n; p++) {
 		const pos_t *q = &b->p[p];
-		/* ascii_only (-i): the exact engine folds bytes >= 0x80 through the ISO-8859-1 LUT (bitap.c:171), which the
-		 * anchors' plain 0x20 fold cannot express -- such bytes never sit inside an anchor */
-		if (q->part != part || q->is_sep || q->lit < 0 || q->lit == '\n' || (ascii_only && q->lit >= 0x80)) { run = 0; continue; }
+		int vals[2];
+		if (q->part != part || !pos_values(q, ascii_only, literal_only, vals)) { run = 0; continue; }
 		if (++run == A) {
-			uint32_t v = 0; int t;
-			for (t = 0; t < A; t++) v |= (uint32_t)(b->p[p - A + 1 + t].lit & 0xFF) << (8 * t);
-			if (n < cap) { where[n] = p - A + 1; out[n++] = v; }
+			piece_t pc; int t, nv = 1, i;
+			pc.where = p - A + 1; pc.v[0] = 0;
+			for (t = 0; t < A && nv; t++) {
+				int vv[2], m = pos_values(&b->p[p - A + 1 + t], ascii_only, literal_only, vv), old = nv;
+				if (nv * m > PIECE_VARIANTS) { nv = 0; break; }
+				for (i = 0; i < old; i++) {
+					const uint32_t base = pc.v[i];
+					pc.v[i] = base | (uint32_t)(vv[0] & 0xFF) << (8 * t);
+					if (m == 2) pc.v[nv++] = base | (uint32_t)(vv[1] & 0xFF) << (8 * t);
+				}
+			}
+			pc.nvar = nv;
+			if (nv && n < cap) out[n++] = pc;
 			run = 0;
 		}
 		if (q->wild) run = 0;     /* '#' behind q: free insertions there, a verbatim run cannot continue through it */
@@ -357,27 +393,37 @@ static int collect_runs(const build_t *b, int part, int A, int ascii_only, uint3
 
 static void plan_anchors(const build_t *b, agb_desc *d, const agb_options *o, int fold_all)
 {
-	int A, p, part;
+	int A, p, part, step;
 	d->plan = AGB_PLAN_ALL; d->n_anchors = 0; d->n_anchors3 = 0; d->adaptive = 1;
 	if (d->inverse || o->ins_free) return;   /* -v reports the NON-matching records; -p makes insertions free */
-	for (A = 4; A >= 2; A--) {
-		uint32_t got[AGB_MAXANCHOR]; int pos[AGB_MAXANCHOR], ngot = 0, ok = 1;
+	/* per anchor length: literal runs first, then runs that may hold two-valued classes (more anchors for the same pieces) */
+	for (step = 0; step < 6; step++) {
+		const int lit_only = !(step & 1);
+		A = 4 - step / 2;
+		uint32_t got[AGB_MAXANCHOR]; int pos[AGB_MAXANCHOR], ngot = 0, ok = 1, classes = 0;
+		piece_t pcs[AGB_MAXANCHOR]; int i, v;
+#define TAKE_PIECES(arr, cnt) do { \
+			for (i = 0; i < (cnt) && ok; i++) for (v = 0; v < (arr)[i].nvar; v++) { \
+				if (ngot >= AGB_MAXANCHOR) { ok = 0; break; } \
+				got[ngot] = (arr)[i].v[v]; pos[ngot++] = (arr)[i].where; if ((arr)[i].nvar > 1) classes = 1; \
+			} } while (0)
 		if (b->or_seen) {                    /* a,b : any alternative may match -> k+1 runs from each */
 			for (part = 1; part <= b->nparts && ok; part++) {
-				uint32_t tmp[AGB_MAXANCHOR]; int tp[AGB_MAXANCHOR], nt = collect_runs(b, part, A, o->nocase || fold_all, tmp, tp, AGB_MAXANCHOR);
-				if (nt < d->k + 1 || ngot + d->k + 1 > AGB_MAXANCHOR) ok = 0;
-				else { memcpy(got + ngot, tmp, sizeof(uint32_t) * (size_t)(d->k + 1)); memcpy(pos + ngot, tp, sizeof(int) * (size_t)(d->k + 1)); ngot += d->k + 1; }
+				int nt = collect_runs(b, part, A, o->nocase || fold_all, lit_only, pcs, AGB_MAXANCHOR);
+				if (nt < d->k + 1) ok = 0; else TAKE_PIECES(pcs, d->k + 1);
 			}
 		} else {                             /* single pattern or a;b (all must match): the part richest in runs */
-			int best = -1;
+			int best = -1, bestpart = 0;
 			for (part = 1; part <= b->nparts; part++) {
-				uint32_t tmp[AGB_MAXANCHOR]; int tp[AGB_MAXANCHOR], nt = collect_runs(b, part, A, o->nocase || fold_all, tmp, tp, AGB_MAXANCHOR);
-				if (nt > best) { best = nt; memcpy(got, tmp, sizeof(uint32_t) * (size_t)nt); memcpy(pos, tp, sizeof(int) * (size_t)nt); }
+				int nt = collect_runs(b, part, A, o->nocase || fold_all, lit_only, pcs, AGB_MAXANCHOR);
+				if (nt > best) { best = nt; bestpart = part; }
 			}
-			if (best < d->k + 1) ok = 0; else ngot = d->k + 1;
+			if (best < d->k + 1) ok = 0;
+			else { collect_runs(b, bestpart, A, o->nocase || fold_all, lit_only, pcs, AGB_MAXANCHOR); TAKE_PIECES(pcs, d->k + 1); }
 		}
+#undef TAKE_PIECES
 		if (!ok) continue;
-		d->plan = AGB_PLAN_ANCHORS; d->n_anchors = ngot; d->anchor_len = A;
+		d->plan = AGB_PLAN_ANCHORS; d->anchor_len = A;
 		d->anchor_mask = (A == 4) ? 0xFFFFFFFFu : (A == 3 ? 0x00FFFFFFu : 0x0000FFFFu);
 		/* case folding: the SAME 0x20 is OR-ed into every byte of the text words and of the anchors (a window
 		 * is cut from two words at any byte offset, so the fold must not depend on the byte lane).  Both
@@ -388,12 +434,19 @@ static void plan_anchors(const build_t *b, agb_desc *d, const agb_options *o, in
 				int t;
 				for (t = 0; t < A; t++) if (is_alpha((int)(got[p] >> (8 * t) & 0xFF))) d->anchor_fold = 0x20202020u;
 			}
-		for (p = 0; p < ngot; p++) d->anchor[p] = (got[p] | d->anchor_fold) & d->anchor_mask;
 		/* stage 1.5: a hit of anchor i at text offset t can only belong to a match inside
 		 * [t - off_i - k, t + pat_len - off_i + k) when the pattern is a single part without '#' */
 		d->pat_len = d->M - d->L - 1;
-		for (p = 0; p < ngot; p++) d->anchor_off[p] = pos[p] - (d->L + 2);
+		d->n_anchors = 0;
+		for (p = 0; p < ngot; p++) {
+			const uint32_t val = (got[p] | d->anchor_fold) & d->anchor_mask; int dup = 0;
+			for (i = 0; i < d->n_anchors; i++) if (d->anchor[i] == val && d->anchor_off[i] == pos[p] - (d->L + 2)) dup = 1;   /* [eE] under -i */
+			if (dup) continue;
+			d->anchor[d->n_anchors] = val; d->anchor_off[d->n_anchors++] = pos[p] - (d->L + 2);
+		}
 		d->refine = (b->nparts == 1 && !b->and_mode && !b->or_seen && d->wildmask == 0) ? 1 : 0;
+		/* the planner in scan.cu re-derives plans from the literal positions alone: not for a plan that leans on classes */
+		if (classes) d->adaptive = 0;
 		return;
 	}
 }

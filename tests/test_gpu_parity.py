@@ -387,3 +387,28 @@ def test_self_overlapping_delimiters(delim):
                 res, got = p.scan_host(d, ordinals=True)
                 assert res.n_matched == cnt and [t[:3] for t in got] == [t[:3] for t in recs], (delim, pat, seed)
                 assert p.scan_host(d, want_records=False)[0].n_matched == cnt
+
+
+def test_class_variant_anchor_plans():
+    """positions that accept two bytes ([ea]) may sit inside an anchor: the piece "b[ea]c" stands in stage 1 as the two
+    anchors "bec" and "bac" at the same place (pattern.c collect_runs) -- patterns with small classes keep the filter path
+    instead of walking every byte.  Lists with ordinals and counts against the oracle, both variants present in the text."""
+    data = _corpus.make_text(4000, seed=21)
+    for a, b_, cnt in ((b"because", b"bacause", 60), (b"state", b"stote", 40), (b"government", b"govarnmant", 30), (b"government", b"governmant", 30),
+                       (b"national", b"notional", 40), (b"order", b"ordar", 40), (b"world", b"warld", 40), (b"people", b"paopla", 40)):
+        parts = data.split(a)
+        step = max(1, len(parts) // cnt)
+        data = b"".join(p + (b_ if i % step == 0 else a) for i, p in enumerate(parts[:-1])) + parts[-1]
+    chunks = len(data) // 16
+    for pat, kw, min_na in (("b[ea]cause", dict(k=1, linenum=1), 3), ("b[ea]cause", dict(k=0, linenum=1), 1), ("st[ao]te", dict(k=0, linenum=1), 2),
+                            ("gov[ea]rnm[ea]nt", dict(k=1, linenum=1), 4),
+                            ("w[oa]rld", dict(k=0, linenum=1, nocase=1), 2), ("p[ea]opl[ea] how", dict(k=2, linenum=1), 4),
+                            ("b[ea]c.u[s-t]e", dict(k=1, linenum=1), 4), ("st[ao]te", dict(k=1, linenum=1, wordbound=1), 2)):
+        p = ag.Pattern(pat, **api_kw(kw))
+        assert p.desc.plan == 1 and p.desc.n_anchors >= min_na, (pat, p.desc.plan, p.desc.n_anchors)
+        a = _oracle.compile(pat, **kw)
+        cnt, recs = _oracle.scan(a, data)
+        res, got = p.scan_host(data, ordinals=True)
+        assert cnt > 5 and res.n_matched == cnt and [t[:3] for t in got] == [t[:3] for t in recs], (pat, kw)
+        assert res.n_flagged < chunks // 4, (pat, res.n_flagged, chunks)
+        assert p.scan_host(data, want_records=False)[0].n_matched == cnt, (pat, kw)
