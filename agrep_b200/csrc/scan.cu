@@ -20,6 +20,7 @@
 #include "scan_internal.cuh"
 #include "corpus.h"
 #include <unistd.h>
+#include <fcntl.h>
 #include <sys/stat.h>
 #include <mutex>
 #include <thread>
@@ -488,8 +489,9 @@ struct SliceSource {
 };
 
 /* a slice of a regular file into the pinned ring: 4 host threads pread(2) a quarter each (one thread's read(2) from the page
- * cache is a third of what PCIe takes) */
-static bool par_pread(int fd, off_t at, uint8_t *dst, size_t len)
+ * cache is a third of what PCIe takes).  direct: fd was opened with O_DIRECT -- whole 4 KiB blocks are asked for (the ring's
+ * buffers are page aligned and a multiple of 4 KiB long; the file's last block comes back short) */
+static bool par_pread(int fd, off_t at, uint8_t *dst, size_t len, bool direct)
 {
 	const int T = 4; const size_t part = ((len + T - 1) / T + 4095) & ~(size_t)4095;
 	std::thread th[T]; int used = 0; std::atomic<int> bad{0};
@@ -499,14 +501,35 @@ static bool par_pread(int fd, off_t at, uint8_t *dst, size_t len)
 		th[used++] = std::thread([=, &bad] {
 			size_t got = 0;
 			while (got < l) {
-				ssize_t r = pread(fd, dst + a + got, l - got, at + (off_t)(a + got));
-				if (r <= 0) { bad = 1; return; }
-				got += (size_t)r;
+				const size_t ask = direct ? ((l - got + 4095) & ~(size_t)4095) : l - got;
+				ssize_t r = pread(fd, dst + a + got, ask, at + (off_t)(a + got));
+				if (r <= 0 || (direct && (size_t)r < l - got && ((size_t)r & 4095))) { bad = 1; return; }
+				got += std::min((size_t)r, l - got);
 			}
 		});
 	}
 	for (int t = 0; t < used; t++) th[t].join();
 	return bad == 0;
+}
+
+/* AGB_ODIRECT=1: read regular files past the page cache (a second descriptor on the same file, through /proc/self/fd);
+ * -1 when not asked for, when the text does not start on a block boundary, or when the file system refuses */
+static int open_direct(int fd, off_t fd_off)
+{
+	const char *e = getenv("AGB_ODIRECT");
+	if (!e || !*e || *e == '0' || (fd_off & 4095)) return -1;
+	char path[64]; snprintf(path, sizeof path, "/proc/self/fd/%d", fd);
+	return open(path, O_RDONLY | O_DIRECT);
+}
+struct FdGuard { int fd = -1; ~FdGuard() { if (fd >= 0) close(fd); } };
+/* one slice of the file into dst; falls back to the caller's own descriptor for good if the direct one fails */
+static bool read_slice(const SliceSource &src, int *dfd, uint64_t off, uint8_t *dst, size_t len)
+{
+	if (*dfd >= 0) {
+		if (par_pread(*dfd, src.fd_off + (off_t)off, dst, len, true)) return true;
+		close(*dfd); *dfd = -1;
+	}
+	return par_pread(src.fd, src.fd_off + (off_t)off, dst, len, false);
 }
 
 static int scan_stream_impl(const agb_desc &d, uint64_t n, const SliceSource &src, int want,
@@ -536,6 +559,8 @@ static int scan_stream_impl(const agb_desc &d, uint64_t n, const SliceSource &sr
 	}
 	rc = ws_upload_desc(W, d, W.s_comp); if (rc) return rc;
 	const bool direct = src.mem && src.pinned;
+	FdGuard dg; if (!src.mem && src.fd >= 0) dg.fd = open_direct(src.fd, src.fd_off);
+	int &dfd = dg.fd;
 	if (!direct && n && !W.stage[0]) for (int i = 0; i < STAGE_BUFS; i++) CUDA_TRY(cudaMallocHost(&W.stage[i], H2D_SLICE));
 	const bool use_front = front_usable(d) && n > 0;
 	const bool count_in_front = use_front && (want & AGB_WANT_ORDINALS) && d.L == 1;
@@ -555,7 +580,7 @@ static int scan_stream_impl(const agb_desc &d, uint64_t n, const SliceSource &sr
 			if (src.mem) par_memcpy(W.stage[sb], src.mem + off, len);
 			else {
 				/* fill_buf(): the slice from the file */
-				if (!par_pread(src.fd, src.fd_off + (off_t)off, W.stage[sb], (size_t)len)) { snprintf(g_err, sizeof g_err, "pread(2) failed or hit the end of the file in [%llu, %llu) of %llu", (unsigned long long)off, (unsigned long long)(off + len), (unsigned long long)n); return AGB_ERR_ARG; }
+				if (!read_slice(src, &dfd, off, W.stage[sb], (size_t)len)) { snprintf(g_err, sizeof g_err, "pread(2) failed or hit the end of the file in [%llu, %llu) of %llu", (unsigned long long)off, (unsigned long long)(off + len), (unsigned long long)n); return AGB_ERR_ARG; }
 			}
 			CUDA_TRY(cudaMemcpyAsync(W.h2d_text + off, W.stage[sb], len, cudaMemcpyHostToDevice, W.s_copy));
 		}
@@ -645,6 +670,8 @@ static int text_upload(const SliceSource &src, uint64_t n, agb_text **out)
 		for (int i = 0; i < STAGE_BUFS; i++) CUDA_TRY(cudaEventCreateWithFlags(&W.ev_copy[i], cudaEventDisableTiming));
 	}
 	const bool direct = src.mem && src.pinned;
+	FdGuard dg; if (!src.mem && src.fd >= 0) dg.fd = open_direct(src.fd, src.fd_off);
+	int &dfd = dg.fd;
 	if (!direct && n && !W.stage[0]) for (int i = 0; i < STAGE_BUFS; i++) CUDA_TRY(cudaMallocHost(&W.stage[i], H2D_SLICE));
 	CUDA_TRY(cudaMemsetAsync(t->d + (n & ~(uint64_t)15), 0, need - (n & ~(uint64_t)15), W.s_copy));
 	const uint64_t n_slices = (n + H2D_SLICE - 1) / H2D_SLICE;
@@ -656,7 +683,7 @@ static int text_upload(const SliceSource &src, uint64_t n, agb_text **out)
 			if (i >= STAGE_BUFS) CUDA_TRY(cudaEventSynchronize(W.ev_copy[sb]));
 			if (src.mem) par_memcpy(W.stage[sb], src.mem + off, len);
 			else {
-				if (!par_pread(src.fd, src.fd_off + (off_t)off, W.stage[sb], (size_t)len)) { snprintf(g_err, sizeof g_err, "pread(2) failed or hit the end of the file in [%llu, %llu) of %llu", (unsigned long long)off, (unsigned long long)(off + len), (unsigned long long)n); cudaStreamSynchronize(W.s_copy); cudaFree(t->d); delete t; return AGB_ERR_ARG; }
+				if (!read_slice(src, &dfd, off, W.stage[sb], (size_t)len)) { snprintf(g_err, sizeof g_err, "pread(2) failed or hit the end of the file in [%llu, %llu) of %llu", (unsigned long long)off, (unsigned long long)(off + len), (unsigned long long)n); cudaStreamSynchronize(W.s_copy); cudaFree(t->d); delete t; return AGB_ERR_ARG; }
 			}
 			CUDA_TRY(cudaMemcpyAsync(t->d + off, W.stage[sb], len, cudaMemcpyHostToDevice, W.s_copy));
 		}

@@ -301,6 +301,21 @@ def test_host_entry_points_agree(tmp_path):
     fd = os.open(str(path), os.O_RDONLY)
     try:
         via(lambda recs, res: L.agb_scan_fd(p._h, fd, _lib.WANT_RECORDS, recs, cap, ctypes.byref(res)))               # regular file
+        assert os.lseek(fd, 0, os.SEEK_CUR) == n                      # the descriptor is left at the end, as read(2) would
+        # the same past the page cache (AGB_ODIRECT=1: a second descriptor with O_DIRECT, whole 4 KiB blocks into the
+        # page-aligned ring, the ragged last block short; silently the plain path where the file system refuses), and
+        # from an offset that is not block aligned (no direct reads then)
+        os.environ["AGB_ODIRECT"] = "1"
+        try:
+            os.lseek(fd, 0, os.SEEK_SET)
+            via(lambda recs, res: L.agb_scan_fd(p._h, fd, _lib.WANT_RECORDS, recs, cap, ctypes.byref(res)))
+            t = ctypes.c_void_p()
+            os.lseek(fd, 0, os.SEEK_SET)
+            assert L.agb_text_from_fd(fd, ctypes.byref(t)) == 0, L.agb_last_error()
+            via(lambda recs, res: L.agb_scan_text(p._h, t, _lib.WANT_RECORDS, recs, cap, ctypes.byref(res)))
+            L.agb_text_free(t)
+        finally:
+            del os.environ["AGB_ODIRECT"]
     finally:
         os.close(fd)
     r, w = os.pipe()
