@@ -329,16 +329,41 @@ __global__ void __launch_bounds__(ORD_THREADS) k_delim_count(const OrdParams P)
  * delimiter appended at EOF, which no block of the text has seen (position n; L = 1 on this path) */
 __global__ void __launch_bounds__(256) k_ord_tiles(const OrdParams P, uint64_t n_tiles)
 {
-	const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	/* a warp per tile: its 64 block counts are 128 consecutive bytes */
+	static_assert(ORD_TILE / ORD_BLOCK == 64, "two block counts per lane");
+	const uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint32_t lane = threadIdx.x & 31;
 	if (t >= n_tiles) return;
-	const uint64_t b0 = t * (ORD_TILE / ORD_BLOCK), eof_blk = P.n / ORD_BLOCK;
-	uint32_t sum = 0;
-	for (uint32_t i = 0; i < ORD_TILE / ORD_BLOCK; i++) {
-		uint32_t v = P.blocks[b0 + i];
-		if (b0 + i == eof_blk) { v += 1; P.blocks[b0 + i] = (uint16_t)v; }
-		sum += v;
+	const uint64_t b = t * 64 + 2 * lane, eof_blk = P.n / ORD_BLOCK;
+	const uint32_t two = *reinterpret_cast<const uint32_t *>(P.blocks + b);
+	uint32_t lo = two & 0xFFFFu, hi = two >> 16;
+	if (b == eof_blk) { lo += 1; P.blocks[b] = (uint16_t)lo; }
+	if (b + 1 == eof_blk) { hi += 1; P.blocks[b + 1] = (uint16_t)hi; }
+	const uint32_t sum = __reduce_add_sync(0xffffffffu, lo + hi);
+	if (lane == 0) P.tiles[t] = sum;
+}
+
+/* delimiter bytes (L = 1) in [from, to), from a multiple of 16: sixteen bytes per load, exact per-byte equality by SWAR;
+ * positions from n on are not text -- the delimiter appended at EOF sits at n */
+__device__ __forceinline__ uint32_t ord_count_swar(const OrdParams &P, int64_t from, int64_t to)
+{
+	const int64_t n = (int64_t)P.n, end = to < n ? to : n;
+	const uint32_t d4 = P.delim[0] * 0x01010101u, f4 = P.dfold[0] * 0x01010101u;
+	uint32_t cnt = (to > n && from <= n) ? 1u : 0u;
+	for (int64_t p = from; p < end; p += 16) {
+		const uint4 x = __ldg(reinterpret_cast<const uint4 *>(P.text + p));
+		const uint32_t xs[4] = { x.x, x.y, x.z, x.w };
+		const int64_t left = end - p;                         /* bytes of this group that count */
+#pragma unroll
+		for (int w = 0; w < 4; w++) {
+			const uint32_t t = (xs[w] | f4) ^ d4;
+			uint32_t z = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t | 0x7F7F7F7Fu);
+			const int64_t v = left - 4 * w;
+			if (v <= 0) z = 0; else if (v < 4) z &= (1u << (8 * (uint32_t)v)) - 1u;
+			cnt += __popc(z);
+		}
 	}
-	P.tiles[t] = sum;
+	return cnt;
 }
 
 __global__ void __launch_bounds__(256) k_ordinals(const OrdParams P)
@@ -351,8 +376,8 @@ __global__ void __launch_bounds__(256) k_ordinals(const OrdParams P)
 	const uint64_t tile = (uint64_t)q / ORD_TILE, blk = (uint64_t)q / ORD_BLOCK;
 	unsigned long long j = P.tile_off[tile];
 	for (uint64_t b = tile * (ORD_TILE / ORD_BLOCK); b < blk; b++) j += P.blocks[b];
-	Reader R; R.init(P.text, P.n, P.delim, P.L);
-	j += ord_count_seq(R, P, (int64_t)(blk * ORD_BLOCK), q + 1);
+	if (P.L == 1) j += ord_count_swar(P, (int64_t)(blk * ORD_BLOCK), q + 1);
+	else { Reader R; R.init(P.text, P.n, P.delim, P.L); j += ord_count_seq(R, P, (int64_t)(blk * ORD_BLOCK), q + 1); }
 	/* the virtual '\n' closes a record of its own when it completes a delimiter: only a 1-byte '\n' can */
 	const long long virt = (P.L == 1 && P.delim[0] == '\n') ? 1 : 0;
 	P.records[i].ordinal = (long long)j + virt + P.j0;
@@ -412,7 +437,7 @@ int ordinals_launch(const agb_desc &d, Workspace &W, const void *d_text, uint64_
 	/* (this one check is byte for byte against the delimiter as typed, also under -i: bitap.c:151-154 compares old_D_pat) */
 	P.j0 = (d.user_delim && d.engine != AGB_ENGINE_ASEARCH0 && n >= (uint64_t)d.L && memcmp(h_head, d.delim, (size_t)d.L) == 0) ? -1 : 0;
 	W.ord_j0 = P.j0;
-	if (blocks_counted) { k_ord_tiles<<<(unsigned)((tiles + 255) / 256), 256, 0, st>>>(P, tiles); g_launches++; }     /* stage 1 counted the blocks */
+	if (blocks_counted) { k_ord_tiles<<<(unsigned)((tiles * 32 + 255) / 256), 256, 0, st>>>(P, tiles); g_launches++; }     /* stage 1 counted the blocks */
 	else { k_delim_count<<<(unsigned)tiles, ORD_THREADS, 0, st>>>(P); g_launches++; }
 	const uint64_t nb = (tiles + SCAN_BLOCK - 1) / SCAN_BLOCK;
 	if (tiles > 4 * SCAN_BLOCK && nb <= W.scan_cap) {
