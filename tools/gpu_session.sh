@@ -1,5 +1,10 @@
 set -x
 cd $GRAFT_REPO_ROOT
-timeout 2400 python -m pytest tests -x -q -m gpu 2>&1 | tail -25 > gpurun_out/r2final2_tests.log
-grep -E "^E|passed|failed" gpurun_out/r2final2_tests.log | head
-timeout 300 python tools/one_scan.py 64 "because each" k=2 list=1 linenum=1 ordinals=1 reps=3 2>&1 | tail -2
+timeout 400 python bench.py > gpurun_out/r2final_bench_n1.json 2> gpurun_out/r2final_bench_n1.err
+python - <<'PY'
+import json
+d=json.loads([l for l in open('gpurun_out/r2final_bench_n1.json') if l.startswith('{')][0])
+print(d['ms_per_step'], d['value'], d['roofline']['frac'], d['roofline_step']['frac'], d['e2e']['value'], d['e2e'].get('fd',{}).get('value'), d['clocks'])
+for s in d['secondary_workloads']: print(s['config'][:50], s['ms'], s['roofline']['frac'])
+PY
+tail -2 gpurun_out/r2final_bench_n1.err
