@@ -113,6 +113,26 @@ def test_anchor_plan():
     assert d.anchor_fold == 0x20202020 and all((d.anchor[i] & d.anchor_fold) == d.anchor_fold for i in range(d.n_anchors))
 
 
+def test_anchor_plan_over_two_valued_classes():
+    """a position that accepts two bytes may sit inside an anchor piece: every spelling of the piece is an anchor at the same
+    place (pattern.c collect_runs); literal runs of the same length are preferred, and the text-sampling planner keeps away"""
+    def anchors(d):
+        return sorted((d.anchor[i].to_bytes(4, "little")[:d.anchor_len], d.anchor_off[i]) for i in range(d.n_anchors))
+    d = ag.Pattern("b[ea]c.u[s-t]e", k=1, linenum=1).desc
+    assert d.plan == ag.api.PLAN_ANCHORS and d.anchor_len == 3 and d.refine == 1 and d.adaptive == 0
+    assert anchors(d) == [(b"bac", 0), (b"bec", 0), (b"use", 4), (b"ute", 4)]
+    d = ag.Pattern("b[ea]cause", linenum=1).desc                      # the literal run "caus" does it alone
+    assert anchors(d) == [(b"caus", 2)] and d.adaptive == 1
+    d = ag.Pattern("ab[cd]efg[hi]jk", k=1, linenum=1).desc            # four-byte pieces with a class beat two-byte literal runs
+    assert anchors(d) == [(b"abce", 0), (b"abde", 0), (b"fghj", 4), (b"fgij", 4)]
+    d = ag.Pattern("[Tt]he [qQ]uick", k=1, nocase=1).desc            # under -i the two cases of a letter are one spelling
+    assert anchors(d) == [(b"quic", 4), (b"the ", 0)]
+    d = ag.Pattern("a[bcd]e[fgh]i[jkl]m", k=1, linenum=1).desc       # three-valued classes break the runs
+    assert d.plan == ag.api.PLAN_ALL
+    d = ag.Pattern("x[ab][cd][ef][gh]y", k=0, linenum=1).desc         # at most four spellings per piece
+    assert d.plan == ag.api.PLAN_ANCHORS and d.n_anchors <= 4
+
+
 def test_corpus_generator_properties():
     c = ag.corpus_host(64 * 4096, needle="because each", needle_every=4, needle_maxedits=3)
     assert len(c) == 64 * 4096 and c.count(b"\0") == 0 and max(c) < 128
@@ -132,10 +152,12 @@ def test_corpus_generator_properties():
     ("state", dict(k=1, linenum=1, delim="$$"), dict(nlines=1500, seed=33, paragraphs=True)),
     ("world", dict(k=1, linenum=1, delim="the"), dict(nlines=600, seed=34)),
     ("governmental", dict(k=5, linenum=1), dict(nlines=1500, seed=35)),
+    ("state", dict(k=1, linenum=1, delim="aba"), "overlap"),            # a delimiter that overlaps itself: taken from the left
+    ("e", dict(k=0, linenum=1, delim="e e"), "overlap"),
 ])
 def test_fill_ordinals_reproduces_j(pattern, kw, corpus_kw):
     """agb_fill_ordinals() (host helper for -n) against the oracle's j, which is pinned to the reference's -n output"""
-    data = _corpus.make_text(**corpus_kw)
+    data = _corpus.overlap_text(kw["delim"], 9) if corpus_kw == "overlap" else _corpus.make_text(**corpus_kw)
     a = _oracle.compile(pattern, **kw)
     cnt, recs = _oracle.scan(a, data)
     assert cnt > 0

@@ -88,3 +88,22 @@ def test_cut_points_are_record_aligned():
         assert cuts[0] == 0 and cuts[-1] == len(text) and cuts == sorted(cuts)
         assert all(text[c - 1] == 10 for c in cuts[1:-1])
     assert shard.page_shards(64 * 4096, 8) == [(r * 8 * 4096, 8 * 4096) for r in range(8)]
+
+
+@pytest.mark.parametrize("delim", ["aba", "e e", "$$x"])
+def test_delimiter_rule_of_the_host_helper(delim):
+    """shard._delim_ends_at (the host-side statement of the device's delimiter rule, used to cut texts in these tests) against
+    the oracle's record ends, for a delimiter that overlaps itself: occurrences are taken from the left, overlapping ones dropped"""
+    if delim == "$$x":
+        delim, dbytes, data = "$$", b"\n\n", _corpus.make_text(300, seed=5, paragraphs=True) + b"\n" * 5 + b"tail state\n"
+    else:
+        dbytes, data = delim.encode(), _corpus.overlap_text(delim, 11)
+    a = _oracle.compile("zzzzqqqq", k=0, linenum=1, inverse=1, delim=delim)          # every record
+    cnt, recs = _oracle.scan(a, data)
+    L = len(dbytes)
+    ends = {e + L - 1 for _, e, _ in recs if e + L - 1 < len(data)}                # last byte of each closing delimiter inside the text
+    mine = {q for q in range(len(data)) if shard._delim_ends_at(data, q, dbytes)}
+    assert cnt > 50 and ends <= mine
+    # closes the oracle does not list are records it drops (empty ones between adjacent delimiters), never a different parse
+    for q in mine - ends:
+        assert shard._delim_ends_at(data, q - L, dbytes) or q - L < 0
