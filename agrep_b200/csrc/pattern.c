@@ -395,7 +395,10 @@ static void plan_anchors(const build_t *b, agb_desc *d, const agb_options *o, in
 {
 	int A, p, part, step;
 	d->plan = AGB_PLAN_ALL; d->n_anchors = 0; d->n_anchors3 = 0; d->adaptive = 1;
-	if (d->inverse || o->ins_free) return;   /* -v reports the NON-matching records; -p makes insertions free */
+	/* -p makes insertions free: no piece need survive.  -v reports the NON-matching records: the anchors cannot point at
+	 * them, so the plan stays AGB_PLAN_ALL -- but the pieces are worked out all the same (see the returns below): a count of
+	 * non-matching records is the number of records minus the matching ones (scan.cu, the complement count) */
+	if (o->ins_free) return;
 	/* per anchor length: literal runs first, then runs that may hold two-valued classes (more anchors for the same pieces) */
 	for (step = 0; step < 6; step++) {
 		const int lit_only = !(step & 1);
@@ -447,6 +450,7 @@ static void plan_anchors(const build_t *b, agb_desc *d, const agb_options *o, in
 		d->refine = (b->nparts == 1 && !b->and_mode && !b->or_seen && d->wildmask == 0) ? 1 : 0;
 		/* the planner in scan.cu re-derives plans from the literal positions alone: not for a plan that leans on classes */
 		if (classes) d->adaptive = 0;
+		if (d->inverse) d->plan = AGB_PLAN_ALL;       /* (the anchors stay in the descriptor for the complement count) */
 		return;
 	}
 }

@@ -413,6 +413,15 @@ static int stages_after_front(const agb_desc &d, Workspace &W, const void *d_tex
 	return AGB_OK;
 }
 
+/* -v, count only: can the answer be had as (records) - (matching records)?  Newline records, one part, no wildcards, an
+ * anchor plan that stage 1.5 can verify (pattern.c keeps the anchors of a -v pattern in the descriptor) */
+static bool complement_usable(const agb_desc &d)
+{
+	if (!d.inverse || d.plan != AGB_PLAN_ALL || d.n_anchors < 1 || d.n_anchors > 9 || d.n_anchors3 || !d.refine) return false;
+	if (d.L != 1 || d.delim[0] != '\n' || d.user_delim || d.delim_fold[0] || d.and_mode || d.wildmask || d.init1 == ~0ull) return false;
+	return true;
+}
+
 int scan_device_impl(const agb_desc &d_in, const void *d_text, uint64_t n, int want, int want_level,
                      agb_record *d_records, uint64_t capacity, cudaStream_t st, agb_result *res, const ShardInfo *sh)
 {
@@ -422,6 +431,24 @@ int scan_device_impl(const agb_desc &d_in, const void *d_text, uint64_t n, int w
 	if ((want & AGB_WANT_RECORDS) && capacity && !d_records) return AGB_ERR_ARG;
 	int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
 	if (dev < 0 || dev >= 64) return AGB_ERR_ARG;
+	if (want == AGB_WANT_COUNT && !sh && n >= (1u << 20) && complement_usable(d_in)) {
+		/* `agrep -c -v pattern`, newline records: every record either matches or does not (the same test at the same close,
+		 * bitap.c:182 with INVERSE flipped), so the count of the non-matching ones is the number of records minus the count of
+		 * the matching ones -- and those the anchors find.  Records: one per newline of the text, one more for an unterminated
+		 * last line (the delimiter appended at EOF closes it; after a final newline it would close the phantom record that
+		 * agrep.c:3811 drops).  The newlines are counted by the same pass (j at EOF = newlines + appended + virtual). */
+		agb_desc pos = d_in; pos.inverse = 0; pos.plan = AGB_PLAN_ANCHORS;
+		agb_result r;
+		int rc = scan_device_impl(pos, d_text, n, AGB_WANT_COUNT | AGB_WANT_ORDINALS, -1, nullptr, 0, st, &r, nullptr); if (rc) return rc;
+		unsigned char last = 0;
+		CUDA_TRY(cudaMemcpyAsync(&last, (const uint8_t *)d_text + n - 1, 1, cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+		const uint64_t records = r.n_closes - 2 + (last != '\n' ? 1 : 0);
+		if (r.n_closes < 2 || r.n_matched > records) { snprintf(g_err, sizeof g_err, "internal: complement count out of range"); return AGB_ERR_CUDA; }
+		*res = r;
+		res->n_matched = records - r.n_matched; res->n_closes = 0; res->n_records = 0;
+		return AGB_OK;
+	}
 	std::lock_guard<std::mutex> lk(g_ws_mu[dev]);
 	Workspace &W = g_ws[dev];
 	int rc = ws_prepare(W, n); if (rc) return rc;

@@ -427,3 +427,31 @@ def test_class_variant_anchor_plans():
         assert cnt > 5 and res.n_matched == cnt and [t[:3] for t in got] == [t[:3] for t in recs], (pat, kw)
         assert res.n_flagged < chunks // 4, (pat, res.n_flagged, chunks)
         assert p.scan_host(data, want_records=False)[0].n_matched == cnt, (pat, kw)
+
+
+def test_inverse_count_by_complement():
+    """`agrep -c -v`, newline records, device-resident text of 1 MiB and more: the number of records minus the number of
+    matching records (scan.cu complement_usable) instead of the automaton over every byte.  Against the oracle; texts with
+    and without a final newline, with blank lines, starting with a newline, ending in a match."""
+    import torch
+    body = _corpus.make_text(40000, seed=78)
+    assert len(body) > (1 << 20) + 4096
+    texts = [body, body[:-1], b"\n\n" + body, body.replace(b"the\n", b"the\n\n\n", 500), body + b"because each", body + b"\n\n\n",
+             body + b"x because each y"]
+    cases = [("because each", dict(k=2, inverse=1, linenum=1)), ("because each", dict(k=0, inverse=1, linenum=1)), ("state", dict(k=1, inverse=1, linenum=1)),
+             ("government", dict(k=3, inverse=1, nocase=1)), ("b[ea]cause", dict(k=1, inverse=1, linenum=1)),
+             ("world", dict(k=1, inverse=1, wordbound=1, linenum=1)), ("because each", dict(k=2, inverse=1, cost_s=2))]
+    for data in texts:
+        t = torch.frombuffer(bytearray(data + b"\0" * 64), dtype=torch.uint8).cuda()
+        chunks = len(data) // 16
+        for pat, kw in cases:
+            try:
+                a = _oracle.compile(pat, **kw)
+            except _oracle.OracleError:
+                continue
+            cnt, _ = _oracle.scan(a, data, want_records=False)
+            p = ag.Pattern(pat, **api_kw(kw))
+            r = p.scan_device(t.data_ptr(), len(data))
+            assert r.n_matched == cnt, (pat, kw, len(data), r.n_matched, cnt)
+            assert r.n_flagged < chunks // 2, (pat, kw, r.n_flagged)              # the complement path ran (the every-byte forms flag all)
+            assert p.scan_host(data, want_records=False)[0].n_matched == cnt       # the streaming entry: the automaton forms
