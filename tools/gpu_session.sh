@@ -1,10 +1,7 @@
 set -x
 cd $GRAFT_REPO_ROOT
-timeout 400 python bench.py > gpurun_out/r2final_bench_n1.json 2> gpurun_out/r2final_bench_n1.err
-python - <<'PY'
-import json
-d=json.loads([l for l in open('gpurun_out/r2final_bench_n1.json') if l.startswith('{')][0])
-print(d['ms_per_step'], d['value'], d['roofline']['frac'], d['roofline_step']['frac'], d['e2e']['value'], d['e2e'].get('fd',{}).get('value'), d['clocks'])
-for s in d['secondary_workloads']: print(s['config'][:50], s['ms'], s['roofline']['frac'])
-PY
-tail -2 gpurun_out/r2final_bench_n1.err
+timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "inverse_count or random_metachar or ragged" 2>&1 | tail -15 > gpurun_out/r2c_tests.log
+grep -E "^E|passed|failed" gpurun_out/r2c_tests.log | head
+timeout 200 python tools/path_bench.py 2>&1 | grep -E "inverse|pattern " 
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -5 > gpurun_out/r2final3_tests.log
+grep -E "^E|passed|failed" gpurun_out/r2final3_tests.log | head
