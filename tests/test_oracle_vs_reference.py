@@ -246,3 +246,22 @@ def test_self_overlapping_delimiters(ref_agrep, delim, pattern, kw, rargs):
             out = run_ref(ref_agrep, ["-n"] + rargs + ["-d", delim, pattern], d)
             # (with a user delimiter -n prints j itself: the record count starts one lower, bitap.c:151-156 / agrep.c:3878)
             assert [r[2] for r in recs] == [int(m.group(1)) for m in re.finditer(rb"(\d+): ", out)], (delim, pattern)
+
+
+@pytest.mark.parametrize("pattern,kw,rargs", [("because each", dict(k=2, linenum=1), ["-2"]), ("state", dict(k=0, linenum=1), []),
+                                              ("gov[ea]rnment", dict(k=1, linenum=1), ["-1"]), ("world", dict(k=1, linenum=1, wordbound=1), ["-1", "-w"])])
+def test_inverse_count_is_records_minus_matches(ref_agrep, pattern, kw, rargs):
+    """what the device's complement count rests on (scan.cu complement_usable): under -v every newline record either matches
+    or does not, so `-c -v` = records - `-c`, with records = newlines + one for an unterminated last line -- checked on the
+    reference binary itself and on the restatement, for texts with blank lines, without a final newline, starting with
+    newlines, ending in a match"""
+    if not ref_agrep:
+        pytest.skip("reference binary not built")
+    body = TEXT[:40000]
+    for data in (body, body[:-1], b"\n\n" + body, body.replace(b"the\n", b"the\n\n\n", 40), body + b"because each", body + b"\n\n\n", b"\n", b"x"):
+        records = data.count(b"\n") + (0 if data.endswith(b"\n") else 1)
+        pos = ref_count(ref_agrep, ["-n"] + rargs + [pattern], data)
+        inv = ref_count(ref_agrep, ["-n", "-v"] + rargs + [pattern], data)
+        assert inv == records - pos, (pattern, len(data), inv, records, pos)
+        a = _oracle.compile(pattern, inverse=1, **kw)
+        assert _oracle.scan(a, data, want_records=False)[0] == inv
