@@ -455,3 +455,22 @@ def test_inverse_count_by_complement():
             assert r.n_matched == cnt, (pat, kw, len(data), r.n_matched, cnt)
             assert r.n_flagged < chunks // 2, (pat, kw, r.n_flagged)              # the complement path ran (the every-byte forms flag all)
             assert p.scan_host(data, want_records=False)[0].n_matched == cnt       # the streaming entry: the automaton forms
+
+
+def test_long_simple_literals_keep_sgrep_semantics():
+    """a simple literal of more than 20 characters at k = 0: the reference runs monkey() instead of bm() (sgrep.c:407-442,
+    1540-1834) with the same record semantics -- ASCII case folded, -w by isalnum neighbours (pinned on the reference binary in
+    test_oracle_vs_reference.py::test_sgrep_long_literals_take_monkey); here the sgrep engine with 64-bit rows on the device."""
+    pat = "homogeneous approximate matching"
+    data = (TEXT[:200000] + b"xx Homogeneous Approximate Matching yy\nno homogeneous approximate matchin here\n"
+            + b"ahomogeneous approximate matching\nthe homogeneous approximate matching.\n" + TEXT[200000:400000]
+            + b"end homogeneous approximate matching")
+    for kw in ({}, dict(wordbound=1), dict(delim=";")):
+        a = _oracle.compile(pat, **kw)
+        assert a.engine == 4
+        d = data.replace(b"\n", b";") if kw.get("delim") else data
+        cnt, recs = _oracle.scan(a, d)
+        p = ag.Pattern(pat, **api_kw(kw))
+        res, got = p.scan_host(d)
+        assert cnt >= 3 and res.n_matched == cnt and [t[:2] for t in got] == [t[:2] for t in recs], (kw, cnt, res.n_matched)
+        assert p.scan_host(d, want_records=False)[0].n_matched == cnt
